@@ -1,0 +1,205 @@
+/* b200vit.h -- C ABI of the B200-native RGA3 visual path.
+ *
+ * One shared library (libb200vit.so, sm_100a) replaces, behind the reference's
+ * own module boundary, everything between "uint8 frames + visual-prompt layer"
+ * and "merged visual embeddings":
+ *
+ *   STOM overlay      /root/reference/model/STOM.py:72-207 (warp :145-160, warp_point :163-207)
+ *                     /root/reference/utils/visual_prompt_generator.py:102-104, :284-363
+ *   normalise+patchify HF transformers video_processing_qwen2_vl.py:239-272,
+ *                     image_processing_backends.py:291-331 (called from
+ *                     /root/reference/utils/dataset.py:77-84)
+ *   vision tower      HF transformers modeling_qwen2_5_vl.py:455-518
+ *                     (Qwen2_5_VisionTransformerPretrainedModel.forward), called by the
+ *                     reference at /root/reference/model/qwen_2_5_vl_sam2.py:182-200, :346-355
+ *
+ * Conventions: plain C, no C++/torch types; every pointer named d_* is a DEVICE
+ * pointer owned by the caller; h_* is a HOST pointer.  All work is enqueued on
+ * the caller's stream, nothing synchronises the host except where stated.
+ * Return 0 on success, a negative B200VIT_E* code otherwise (never aborts, never
+ * falls back to a CPU path); b200vit_last_error() gives the thread-local message.
+ */
+#ifndef B200VIT_H_
+#define B200VIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VIT_VERSION 1
+
+enum {
+  B200VIT_OK = 0,
+  B200VIT_EINVAL = -1,   /* bad shape / argument                         */
+  B200VIT_EALIGN = -2,   /* pointer or leading dimension not 16-B aligned */
+  B200VIT_EARCH = -3,    /* device is not sm_100                          */
+  B200VIT_ECUDA = -4,    /* CUDA runtime / driver error                   */
+  B200VIT_ENOMEM = -5    /* workspace too small                           */
+};
+
+typedef void* b200vit_stream; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ config
+ * Mirrors Qwen2_5_VLVisionConfig (HF configuration_qwen2_5_vl.py:37-63).      */
+typedef struct b200vit_cfg {
+  int32_t depth, hidden, intermediate, heads, out_hidden;
+  int32_t patch, temporal_patch, merge, window, in_channels;
+  int32_t n_fullatt;
+  int32_t fullatt[64];
+} b200vit_cfg;
+
+/* ------------------------------------------------------------------ plan
+ * Everything that depends only on grid_thw: window_index / reverse index
+ * (HF modeling :411-451, :512), cu_seqlens (:488-496), cu_window_seqlens
+ * (:476), rope cos/sin tables in window order (:382-409, :485-486), attention
+ * work lists, workspace layout.  Host part is computed at create time (no GPU
+ * needed); device copies are uploaded lazily by the first forward.           */
+typedef struct b200vit_plan b200vit_plan;
+
+int b200vit_version(void);
+const char* b200vit_last_error(void);
+
+int b200vit_plan_create(const int64_t* h_grid_thw, int n_grids, const b200vit_cfg* cfg, b200vit_plan** out);
+void b200vit_plan_destroy(b200vit_plan* plan);
+
+enum {
+  B200VIT_PLAN_M = 0,              /* int64 [1]   number of patches                      */
+  B200VIT_PLAN_WINDOW_INDEX = 1,   /* int64 [M/4] HF window_index                        */
+  B200VIT_PLAN_REVERSE_INDEX = 2,  /* int64 [M/4] argsort(window_index)                  */
+  B200VIT_PLAN_CU_WINDOW = 3,      /* int32 [...] cu_window_seqlens after unique_consecutive */
+  B200VIT_PLAN_CU_FULL = 4,        /* int32 [...] cu_seqlens                             */
+  B200VIT_PLAN_ROW_MAP = 5,        /* int32 [M]   patch row -> row in window order       */
+  B200VIT_PLAN_ROPE_COS = 6,       /* fp32  [M,head_dim/2] window order                  */
+  B200VIT_PLAN_ROPE_SIN = 7,       /* fp32  [M,head_dim/2] window order                  */
+  B200VIT_PLAN_POS_IDS = 8         /* int32 [M,2] (hpos,wpos), ORIGINAL patch order       */
+};
+/* Copies a host-side plan array into h_dst (cap bytes).  Returns the number of
+ * bytes the array holds (so a call with cap = 0 sizes it), negative on error.  */
+int64_t b200vit_plan_get(const b200vit_plan* plan, int which, void* h_dst, size_t cap);
+size_t b200vit_workspace_bytes(const b200vit_plan* plan);
+
+/* ------------------------------------------------------------------ weights
+ * Packed once by the host module (rga3-release_b200/module.py::pack_weights)
+ * from the HF state_dict; all bf16 matrices are [N, K] row-major (nn.Linear
+ * layout), K padded as noted.                                                */
+typedef struct b200vit_layer_weights {
+  const float* norm1_w;     /* [D]                                                      */
+  const void* qkv_w;        /* bf16 [3D, D]                                             */
+  const float* qkv_b;       /* [3D]                                                     */
+  const void* proj_w;       /* bf16 [D, D]                                              */
+  const float* proj_b;      /* [D]                                                      */
+  const float* norm2_w;     /* [D]                                                      */
+  const void* gateup_w;     /* bf16 [2*Ipad, D], rows interleaved g0,u0,g1,u1,...        */
+  const float* gateup_b;    /* [2*Ipad] interleaved the same way                         */
+  const void* down_w;       /* bf16 [D, Ipad] (zero columns beyond I)                    */
+  const float* down_b;      /* [D]                                                      */
+} b200vit_layer_weights;
+
+typedef struct b200vit_weights {
+  const void* patch_w;      /* bf16 [D, C*tp*p*p] (Conv3d weight viewed 2-D, HF :106-114) */
+  const b200vit_layer_weights* layers; /* HOST array [depth] of device pointers          */
+  const float* merger_ln_w; /* [D]                                                      */
+  const void* merger_fc1_w; /* bf16 [4D, 4D]                                            */
+  const float* merger_fc1_b;
+  const void* merger_fc2_w; /* bf16 [out_hidden, 4D]                                    */
+  const float* merger_fc2_b;
+  int32_t ipad;             /* padded intermediate size (multiple of 128)               */
+} b200vit_weights;
+
+/* ------------------------------------------------------------------ overlay
+ * Output of the STOM policy (/root/reference/model/STOM.py:72-141), which stays
+ * on the host: which frames get the prompt layer and how it is moved.         */
+enum { B200VIT_LAYER_NONE = 0, B200VIT_LAYER_RGBA = 1, B200VIT_LAYER_PALETTE = 2, B200VIT_LAYER_BOX = 3 };
+enum { B200VIT_FRAME_NONE = 0, B200VIT_FRAME_LAYER = 1, B200VIT_FRAME_CIRCLE = 2 };
+
+typedef struct b200vit_frame_op {
+  int32_t mode;        /* B200VIT_FRAME_*                                             */
+  int32_t sx, sy;      /* integer translation of the layer (STOM.warp, :145-155)      */
+  int32_t zx, zy;      /* 1: extra truncation-toward-zero source for column/row 0     */
+  int32_t cx, cy, r;   /* circle stamp of STOM.warp_point (:195-201)                  */
+  uint8_t rgba[4];     /* circle colour (alpha already clamped, :174)                  */
+} b200vit_frame_op;
+
+typedef struct b200vit_overlay {
+  int32_t kind;                 /* B200VIT_LAYER_*                                     */
+  const uint8_t* d_layer;       /* RGBA: [H,W,4]; PALETTE: [H,W] indices, 0 = clear     */
+  uint8_t palette[256][4];      /* PALETTE colours; BOX colour in palette[1]           */
+  int32_t box[4];               /* BOX: l,t,r,b inclusive (PIL rectangle)              */
+  int32_t box_width;
+  const b200vit_frame_op* h_ops; /* HOST array [T]; circle stamps of one clip share r   */
+} b200vit_overlay;
+
+typedef struct b200vit_frames {
+  const uint8_t* d_frames;  /* uint8 [T,H,W,3] (HWC, what PIL / cv2 decode produce)    */
+  int32_t t, h, w;          /* T may be odd: last frame repeated (HF videoproc :245-249) */
+} b200vit_frames;
+
+/* ------------------------------------------------------------------ hot path */
+/* Whole path.  Exactly one of d_pixel_values (bf16 [M, C*tp*p*p], the HF
+ * processor's layout) and frames (+ optional overlay) is non-NULL; frames are
+ * only valid for a single-grid plan.  d_out: [M/4, out_hidden], bf16
+ * (out_f32 = 0) or fp32, in ORIGINAL merged-token order.  d_last_hidden
+ * (optional, may be NULL): fp32 [M, D] in window order (HF 5.x
+ * last_hidden_state).                                                         */
+int b200vit_forward(b200vit_plan* plan, const b200vit_weights* w, const void* d_pixel_values,
+                    const b200vit_frames* frames, const b200vit_overlay* overlay, void* d_out, int out_f32,
+                    float* d_last_hidden, void* d_workspace, size_t workspace_bytes, b200vit_stream stream);
+
+/* Number of kernel launches one b200vit_forward enqueues for this plan.       */
+int b200vit_forward_launches(const b200vit_plan* plan, int with_frames);
+
+/* ------------------------------------------------------------------ single ops
+ * The kernels behind b200vit_forward, exposed for parity tests and profiling. */
+
+/* Overlay only: composited uint8 frames [T,H,W,3] (bit-exact vs PIL).         */
+int b200vit_overlay_composite(const b200vit_frames* frames, const b200vit_overlay* overlay, uint8_t* d_out,
+                              b200vit_stream stream);
+/* Overlay + normalise + patchify: bf16 [M, 3*tp*14*14] in processor order.    */
+int b200vit_overlay_patchify(const b200vit_frames* frames, const b200vit_overlay* overlay, int patch, int tps,
+                             int merge, void* d_out_bf16, b200vit_stream stream);
+
+enum {
+  B200VIT_EPI_STORE_F32 = 0,     /* out_f32[row_map[r]] = acc                                 */
+  B200VIT_EPI_QKV_ROPE = 1,      /* bf16 out = rope(acc + bias) for cols < 2D, acc + bias after */
+  B200VIT_EPI_BIAS_RESIDUAL = 2, /* out_f32 += acc + bias                                     */
+  B200VIT_EPI_SWIGLU = 3,        /* bf16 out[:, c/2] = silu(acc[c]+b[c]) * (acc[c+1]+b[c+1])   */
+  B200VIT_EPI_BIAS_GELU = 4,     /* bf16 out = gelu_erf(acc + bias)                           */
+  B200VIT_EPI_BIAS_BF16 = 5,     /* bf16 out[row_map[r]] = acc + bias                         */
+  B200VIT_EPI_BIAS_F32 = 6       /* f32  out[row_map[r]] = acc + bias                         */
+};
+typedef struct b200vit_gemm_args {
+  const void* d_a;      /* bf16 [M, K] row-major, lda = K                              */
+  const void* d_b;      /* bf16 [N, K] row-major (nn.Linear weight)                    */
+  void* d_out;          /* see epilogue                                               */
+  const float* d_bias;  /* [N] or NULL                                                */
+  const int32_t* d_row_map; /* [M] or NULL (identity)                                  */
+  const float* d_cos;   /* QKV_ROPE: [M, 40]                                          */
+  const float* d_sin;
+  int32_t m, n, k;
+  int32_t ldo;          /* leading dimension of out, in elements                       */
+  int32_t rope_cols;    /* QKV_ROPE: columns [0, rope_cols) are rotated (= 2D)         */
+  int32_t epilogue;     /* B200VIT_EPI_*                                              */
+} b200vit_gemm_args;
+/* out = epilogue(A[M,K] * B[N,K]^T): tcgen05/TMEM GEMM fed by TMA.             */
+int b200vit_gemm(const b200vit_gemm_args* args, b200vit_stream stream);
+
+/* h_bf16[r,:] = (x[r,:] * rsqrt(mean(x^2)+eps)) * w   (HF modeling :66-71)     */
+int b200vit_rmsnorm(const float* d_x, const float* d_w, void* d_out_bf16, int rows, int dim, float eps,
+                    b200vit_stream stream);
+
+/* Varlen attention over cu_seqlens segments (HF modeling :244-283): qkv bf16
+ * [M, 3*heads*80] (Q|K|V, head-major, RoPE already applied), out bf16 [M, heads*80]. */
+int b200vit_attention(const void* d_qkv, void* d_out, const int32_t* h_cu_seqlens, int n_segments, int heads,
+                      b200vit_stream stream);
+
+/* fp32 / fp16 / bf16 [n] -> bf16 [n] (the `.type(self.visual.dtype)` at HF :1148) */
+int b200vit_cast_to_bf16(const void* d_in, int in_dtype /*0 f32, 1 f16, 2 bf16*/, void* d_out, int64_t n,
+                         b200vit_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VIT_H_ */

@@ -1,0 +1,11 @@
+"""B200-native visual path for RGA3 (STOM overlay -> patchify -> Qwen2.5-VL vision tower).
+
+Python host side of libb200vit.so; see include/b200vit.h, DESIGN.md, INTEGRATION.md.
+"""
+from . import _lib
+from ._lib import B200VitError, lib
+from .module import B200VisionTower, install
+from .overlay import FrameOp, OverlaySpec, shift_from_flow, stom_frame_ops
+
+__all__ = ["B200VisionTower", "install", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "lib",
+           "B200VitError"]

@@ -1,0 +1,386 @@
+// C ABI: plan (everything derived from grid_thw), the whole-path forward and the
+// single-op entry points.  See include/b200vit.h for the contract.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "internal.h"
+
+using namespace b200;
+
+struct b200vit_plan {
+  b200vit_cfg cfg;
+  std::vector<int64_t> grid;  // n*3
+  int64_t m = 0;              // patches
+  int unit = 4;
+  int head_dim = 80;
+  // host arrays
+  std::vector<int64_t> window_index, reverse_index;
+  std::vector<int32_t> cu_window, cu_full, row_map, merge_map, pos_ids;
+  std::vector<float> rope_cos, rope_sin;  // [M, head_dim/2] in window order
+  std::vector<AttnWork> work_window, work_full;
+  // workspace layout (byte offsets)
+  size_t off_x = 0, off_h = 0, off_qkv = 0, off_attn = 0, off_act = 0, off_pv = 0, ws_bytes = 0;
+  int ipad = 0, kpe = 0;
+  // device copies (lazy)
+  std::mutex mu;
+  bool uploaded = false;
+  int32_t* d_row_map = nullptr;
+  int32_t* d_merge_map = nullptr;
+  float* d_cos = nullptr;
+  float* d_sin = nullptr;
+  AttnWork* d_work_window = nullptr;
+  AttnWork* d_work_full = nullptr;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void build_work(const std::vector<int32_t>& cu, std::vector<AttnWork>& out) {
+  out.clear();
+  for (size_t i = 0; i + 1 < cu.size(); ++i) {
+    const int s = cu[i], e = cu[i + 1];
+    for (int q0 = s; q0 < e; q0 += 64) out.push_back(AttnWork{q0, std::min(64, e - q0), s, e - s});
+  }
+}
+
+// HF modeling_qwen2_5_vl.py:411-451 (get_window_index) + :476 (unique_consecutive)
+void build_window_index(b200vit_plan& p) {
+  const b200vit_cfg& c = p.cfg;
+  const int win = c.window / c.merge / c.patch;
+  int64_t base = 0;
+  std::vector<int32_t> cu_raw{0};
+  for (size_t gi = 0; gi < p.grid.size() / 3; ++gi) {
+    const int64_t t = p.grid[gi * 3], h = p.grid[gi * 3 + 1], w = p.grid[gi * 3 + 2];
+    const int64_t lh = h / c.merge, lw = w / c.merge;
+    const int64_t pad_h = win - lh % win, pad_w = win - lw % win;  // a full extra window when divisible (:424-425)
+    const int64_t nwh = (lh + pad_h) / win, nww = (lw + pad_w) / win;
+    for (int64_t ti = 0; ti < t; ++ti)
+      for (int64_t wh = 0; wh < nwh; ++wh)
+        for (int64_t ww = 0; ww < nww; ++ww) {
+          int cnt = 0;
+          for (int ih = 0; ih < win; ++ih)
+            for (int iw = 0; iw < win; ++iw) {
+              const int64_t y = wh * win + ih, x = ww * win + iw;
+              if (y < lh && x < lw) {
+                p.window_index.push_back(base + ti * lh * lw + y * lw + x);
+                ++cnt;
+              }
+            }
+          cu_raw.push_back(cu_raw.back() + cnt * p.unit);
+        }
+    base += t * lh * lw;
+  }
+  p.cu_window.clear();
+  for (int32_t v : cu_raw)
+    if (p.cu_window.empty() || p.cu_window.back() != v) p.cu_window.push_back(v);
+  p.reverse_index.assign(p.window_index.size(), 0);
+  for (size_t i = 0; i < p.window_index.size(); ++i) p.reverse_index[p.window_index[i]] = static_cast<int64_t>(i);
+}
+
+// HF :382-409 (rot_pos_emb), :117-130 (inv_freq), :482-486 (reorder, cos/sin)
+void build_rope(b200vit_plan& p) {
+  const b200vit_cfg& c = p.cfg;
+  const int half = p.head_dim / 2;   // rotary table width (40)
+  const int nfreq = half / 2;        // 20 frequencies per axis
+  std::vector<float> inv_freq(nfreq);
+  for (int k = 0; k < nfreq; ++k) inv_freq[k] = 1.0f / powf(10000.0f, static_cast<float>(2 * k) / static_cast<float>(half));
+  p.pos_ids.resize(p.m * 2);
+  p.rope_cos.resize(p.m * half);
+  p.rope_sin.resize(p.m * half);
+  int64_t r = 0;
+  const int mg = c.merge;
+  for (size_t gi = 0; gi < p.grid.size() / 3; ++gi) {
+    const int64_t t = p.grid[gi * 3], h = p.grid[gi * 3 + 1], w = p.grid[gi * 3 + 2];
+    for (int64_t ti = 0; ti < t; ++ti)
+      for (int64_t bh = 0; bh < h / mg; ++bh)
+        for (int64_t bw = 0; bw < w / mg; ++bw)
+          for (int ih = 0; ih < mg; ++ih)
+            for (int iw = 0; iw < mg; ++iw, ++r) {
+              const int hp = static_cast<int>(bh * mg + ih), wp = static_cast<int>(bw * mg + iw);
+              p.pos_ids[r * 2] = hp;
+              p.pos_ids[r * 2 + 1] = wp;
+              const int64_t dst = p.row_map[r];
+              for (int k = 0; k < nfreq; ++k) {
+                const float ah = static_cast<float>(hp) * inv_freq[k], aw = static_cast<float>(wp) * inv_freq[k];
+                p.rope_cos[dst * half + k] = cosf(ah);
+                p.rope_sin[dst * half + k] = sinf(ah);
+                p.rope_cos[dst * half + nfreq + k] = cosf(aw);
+                p.rope_sin[dst * half + nfreq + k] = sinf(aw);
+              }
+            }
+  }
+}
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+  if (src.empty()) return 0;
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T)));
+  B200_CUDA_OK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int ensure_uploaded(b200vit_plan* p) {
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (p->uploaded) return 0;
+  int rc;
+  if ((rc = upload(&p->d_row_map, p->row_map))) return rc;
+  if ((rc = upload(&p->d_merge_map, p->merge_map))) return rc;
+  if ((rc = upload(&p->d_cos, p->rope_cos))) return rc;
+  if ((rc = upload(&p->d_sin, p->rope_sin))) return rc;
+  if ((rc = upload(&p->d_work_window, p->work_window))) return rc;
+  if ((rc = upload(&p->d_work_full, p->work_full))) return rc;
+  p->uploaded = true;
+  return 0;
+}
+
+bool is_fullatt(const b200vit_cfg& c, int layer) {
+  for (int i = 0; i < c.n_fullatt; ++i)
+    if (c.fullatt[i] == layer) return true;
+  return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200vit_plan_create(const int64_t* h_grid_thw, int n_grids, const b200vit_cfg* cfg, b200vit_plan** out) {
+  if (!h_grid_thw || n_grids <= 0 || !cfg || !out) return fail(B200VIT_EINVAL, "plan_create: null argument");
+  const b200vit_cfg& c = *cfg;
+  if (c.depth <= 0 || c.hidden <= 0 || c.heads <= 0 || c.hidden % c.heads) return fail(B200VIT_EINVAL, "plan_create: bad hidden/heads");
+  if (c.hidden / c.heads != 80) return fail(B200VIT_EINVAL, "plan_create: kernels are specialised for head_dim 80 (all Qwen2.5-VL towers)");
+  if (c.merge <= 0 || c.patch <= 0 || c.temporal_patch <= 0 || c.window % (c.merge * c.patch) || c.window / c.merge / c.patch <= 0)
+    return fail(B200VIT_EINVAL, "plan_create: bad patch/merge/window");
+  if (c.n_fullatt < 0 || c.n_fullatt > 64) return fail(B200VIT_EINVAL, "plan_create: bad fullatt list");
+  if (c.hidden % 8 || c.out_hidden % 8 || c.intermediate <= 0) return fail(B200VIT_EINVAL, "plan_create: dims must be multiples of 8");
+  if ((c.in_channels * c.temporal_patch * c.patch * c.patch) % 8) return fail(B200VIT_EINVAL, "plan_create: patch vector length must be a multiple of 8");
+  b200vit_plan* p = new (std::nothrow) b200vit_plan();
+  if (!p) return fail(B200VIT_ENOMEM, "plan_create: out of host memory");
+  p->cfg = c;
+  p->unit = c.merge * c.merge;
+  p->head_dim = c.hidden / c.heads;
+  p->grid.assign(h_grid_thw, h_grid_thw + 3 * n_grids);
+  for (int i = 0; i < n_grids; ++i) {
+    const int64_t t = h_grid_thw[i * 3], h = h_grid_thw[i * 3 + 1], w = h_grid_thw[i * 3 + 2];
+    if (t <= 0 || h <= 0 || w <= 0 || h % c.merge || w % c.merge) {
+      delete p;
+      return fail(B200VIT_EINVAL, "plan_create: grid_thw entries must be positive with h, w multiples of merge size");
+    }
+    p->m += t * h * w;
+  }
+  if (p->m > (int64_t(1) << 30)) {
+    delete p;
+    return fail(B200VIT_EINVAL, "plan_create: too many patches");
+  }
+  build_window_index(*p);
+  // HF :488-496
+  p->cu_full.push_back(0);
+  for (int i = 0; i < n_grids; ++i)
+    for (int64_t ti = 0; ti < h_grid_thw[i * 3]; ++ti)
+      p->cu_full.push_back(p->cu_full.back() + static_cast<int32_t>(h_grid_thw[i * 3 + 1] * h_grid_thw[i * 3 + 2]));
+  // patch row r (group r/unit) lands at window-order row reverse[group]*unit + r%unit  (HF :478-481)
+  p->row_map.resize(p->m);
+  for (int64_t r = 0; r < p->m; ++r)
+    p->row_map[r] = static_cast<int32_t>(p->reverse_index[r / p->unit] * p->unit + r % p->unit);
+  // merged row i (window order) returns to original position window_index[i]  (HF :512-513)
+  p->merge_map.resize(p->window_index.size());
+  for (size_t i = 0; i < p->window_index.size(); ++i) p->merge_map[i] = static_cast<int32_t>(p->window_index[i]);
+  build_rope(*p);
+  build_work(p->cu_window, p->work_window);
+  build_work(p->cu_full, p->work_full);
+  // workspace
+  p->ipad = static_cast<int>(align_up(c.intermediate, 128));
+  p->kpe = c.in_channels * c.temporal_patch * c.patch * c.patch;
+  const size_t M = static_cast<size_t>(p->m), D = c.hidden;
+  size_t off = 0;
+  p->off_x = off, off = align_up(off + M * D * 4, 1024);
+  p->off_h = off, off = align_up(off + M * D * 2, 1024);
+  p->off_qkv = off, off = align_up(off + M * 3 * D * 2, 1024);
+  p->off_attn = off, off = align_up(off + M * D * 2, 1024);
+  p->off_act = off, off = align_up(off + M * p->ipad * 2, 1024);
+  p->off_pv = off, off = align_up(off + M * p->kpe * 2, 1024);
+  p->ws_bytes = off;
+  *out = p;
+  return 0;
+}
+
+void b200vit_plan_destroy(b200vit_plan* p) {
+  if (!p) return;
+  cudaFree(p->d_row_map);
+  cudaFree(p->d_merge_map);
+  cudaFree(p->d_cos);
+  cudaFree(p->d_sin);
+  cudaFree(p->d_work_window);
+  cudaFree(p->d_work_full);
+  delete p;
+}
+
+int64_t b200vit_plan_get(const b200vit_plan* p, int which, void* h_dst, size_t cap) {
+  if (!p) return fail(B200VIT_EINVAL, "plan_get: null plan");
+  const void* src = nullptr;
+  size_t bytes = 0;
+  switch (which) {
+    case B200VIT_PLAN_M: src = &p->m, bytes = sizeof(int64_t); break;
+    case B200VIT_PLAN_WINDOW_INDEX: src = p->window_index.data(), bytes = p->window_index.size() * 8; break;
+    case B200VIT_PLAN_REVERSE_INDEX: src = p->reverse_index.data(), bytes = p->reverse_index.size() * 8; break;
+    case B200VIT_PLAN_CU_WINDOW: src = p->cu_window.data(), bytes = p->cu_window.size() * 4; break;
+    case B200VIT_PLAN_CU_FULL: src = p->cu_full.data(), bytes = p->cu_full.size() * 4; break;
+    case B200VIT_PLAN_ROW_MAP: src = p->row_map.data(), bytes = p->row_map.size() * 4; break;
+    case B200VIT_PLAN_ROPE_COS: src = p->rope_cos.data(), bytes = p->rope_cos.size() * 4; break;
+    case B200VIT_PLAN_ROPE_SIN: src = p->rope_sin.data(), bytes = p->rope_sin.size() * 4; break;
+    case B200VIT_PLAN_POS_IDS: src = p->pos_ids.data(), bytes = p->pos_ids.size() * 4; break;
+    default: return fail(B200VIT_EINVAL, "plan_get: unknown array id");
+  }
+  if (h_dst && cap >= bytes) std::memcpy(h_dst, src, bytes);
+  return static_cast<int64_t>(bytes);
+}
+
+size_t b200vit_workspace_bytes(const b200vit_plan* p) { return p ? p->ws_bytes : 0; }
+
+int b200vit_forward_launches(const b200vit_plan* p, int with_frames) {
+  if (!p) return 0;
+  const int t_pad_windows = 1;  // one overlay/patchify launch per 128 frames; clips here are <= 128 frames
+  return (with_frames ? t_pad_windows : 0) + 1 + p->cfg.depth * 7 + 3;
+}
+
+int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pixel_values, const b200vit_frames* frames,
+                    const b200vit_overlay* overlay, void* d_out, int out_f32, float* d_last_hidden, void* d_workspace,
+                    size_t workspace_bytes, b200vit_stream stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!p || !w || !d_out || !d_workspace) return fail(B200VIT_EINVAL, "forward: null argument");
+  if ((d_pixel_values == nullptr) == (frames == nullptr))
+    return fail(B200VIT_EINVAL, "forward: pass exactly one of d_pixel_values and frames");
+  if (workspace_bytes < p->ws_bytes) return fail(B200VIT_ENOMEM, "forward: workspace smaller than b200vit_workspace_bytes()");
+  if (reinterpret_cast<uintptr_t>(d_workspace) & 1023) return fail(B200VIT_EALIGN, "forward: workspace must be 1024-byte aligned");
+  int rc = check_arch();
+  if (rc) return rc;
+  if ((rc = ensure_uploaded(p))) return rc;
+  const b200vit_cfg& c = p->cfg;
+  if (w->ipad != p->ipad) return fail(B200VIT_EINVAL, "forward: weights packed with a different intermediate padding");
+  const int M = static_cast<int>(p->m), D = c.hidden;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
+  float* x = reinterpret_cast<float*>(ws + p->off_x);
+  void* h = ws + p->off_h;
+  void* qkv = ws + p->off_qkv;
+  void* attn = ws + p->off_attn;
+  void* act = ws + p->off_act;
+  void* pv = ws + p->off_pv;
+
+  const void* a0 = d_pixel_values;
+  if (frames) {
+    if (p->grid.size() != 3) return fail(B200VIT_EINVAL, "forward: the frames entry takes a single-clip plan");
+    const int64_t t_need = p->grid[0] * c.temporal_patch;
+    if (frames->h != p->grid[1] * c.patch || frames->w != p->grid[2] * c.patch ||
+        (frames->t != t_need && frames->t != t_need - (c.temporal_patch - 1)))
+      return fail(B200VIT_EINVAL, "forward: frames shape does not match the plan's grid_thw");
+    if ((rc = launch_overlay_patchify(*frames, overlay, c.patch, c.temporal_patch, c.merge, pv, nullptr, stream))) return rc;
+    a0 = pv;
+  }
+  b200vit_gemm_args g;
+  std::memset(&g, 0, sizeof(g));
+  // patch embed (+ window reorder in the store)
+  g.d_a = a0, g.d_b = w->patch_w, g.d_out = x, g.d_row_map = p->d_row_map;
+  g.m = M, g.n = D, g.k = p->kpe, g.ldo = D, g.epilogue = B200VIT_EPI_STORE_F32;
+  if ((rc = launch_gemm(g, stream))) return rc;
+
+  for (int l = 0; l < c.depth; ++l) {
+    const b200vit_layer_weights& lw = w->layers[l];
+    const bool full = is_fullatt(c, l);
+    if ((rc = launch_rmsnorm(x, lw.norm1_w, h, M, D, 1e-6f, stream))) return rc;
+    std::memset(&g, 0, sizeof(g));
+    g.d_a = h, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_cos = p->d_cos, g.d_sin = p->d_sin;
+    g.m = M, g.n = 3 * D, g.k = D, g.ldo = 3 * D, g.rope_cols = 2 * D, g.epilogue = B200VIT_EPI_QKV_ROPE;
+    if ((rc = launch_gemm(g, stream))) return rc;
+    if ((rc = launch_attention(qkv, attn, full ? p->d_work_full : p->d_work_window,
+                               static_cast<int>(full ? p->work_full.size() : p->work_window.size()), c.heads, stream)))
+      return rc;
+    std::memset(&g, 0, sizeof(g));
+    g.d_a = attn, g.d_b = lw.proj_w, g.d_out = x, g.d_bias = lw.proj_b;
+    g.m = M, g.n = D, g.k = D, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
+    if ((rc = launch_gemm(g, stream))) return rc;
+    if ((rc = launch_rmsnorm(x, lw.norm2_w, h, M, D, 1e-6f, stream))) return rc;
+    std::memset(&g, 0, sizeof(g));
+    g.d_a = h, g.d_b = lw.gateup_w, g.d_out = act, g.d_bias = lw.gateup_b;
+    g.m = M, g.n = 2 * p->ipad, g.k = D, g.ldo = p->ipad, g.epilogue = B200VIT_EPI_SWIGLU;
+    if ((rc = launch_gemm(g, stream))) return rc;
+    std::memset(&g, 0, sizeof(g));
+    g.d_a = act, g.d_b = lw.down_w, g.d_out = x, g.d_bias = lw.down_b;
+    g.m = M, g.n = D, g.k = p->ipad, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
+    if ((rc = launch_gemm(g, stream))) return rc;
+  }
+  if (d_last_hidden)
+    B200_CUDA_OK(cudaMemcpyAsync(d_last_hidden, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
+  // merger (HF :133-146) + un-reorder (:512-513)
+  const int Mm = M / p->unit, Dm = D * p->unit;
+  if ((rc = launch_rmsnorm(x, w->merger_ln_w, h, M, D, 1e-6f, stream))) return rc;
+  std::memset(&g, 0, sizeof(g));
+  g.d_a = h, g.d_b = w->merger_fc1_w, g.d_out = attn, g.d_bias = w->merger_fc1_b;
+  g.m = Mm, g.n = Dm, g.k = Dm, g.ldo = Dm, g.epilogue = B200VIT_EPI_BIAS_GELU;
+  if ((rc = launch_gemm(g, stream))) return rc;
+  std::memset(&g, 0, sizeof(g));
+  g.d_a = attn, g.d_b = w->merger_fc2_w, g.d_out = d_out, g.d_bias = w->merger_fc2_b, g.d_row_map = p->d_merge_map;
+  g.m = Mm, g.n = c.out_hidden, g.k = Dm, g.ldo = c.out_hidden;
+  g.epilogue = out_f32 ? B200VIT_EPI_BIAS_F32 : B200VIT_EPI_BIAS_BF16;
+  if ((rc = launch_gemm(g, stream))) return rc;
+  return 0;
+}
+
+// ---------------------------------------------------------------- single ops
+int b200vit_overlay_composite(const b200vit_frames* frames, const b200vit_overlay* overlay, uint8_t* d_out,
+                              b200vit_stream stream) {
+  if (!frames || !d_out) return fail(B200VIT_EINVAL, "overlay_composite: null argument");
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_overlay_patchify(*frames, overlay, 14, 2, 2, nullptr, d_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200vit_overlay_patchify(const b200vit_frames* frames, const b200vit_overlay* overlay, int patch, int tps, int merge,
+                             void* d_out_bf16, b200vit_stream stream) {
+  if (!frames || !d_out_bf16) return fail(B200VIT_EINVAL, "overlay_patchify: null argument");
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_overlay_patchify(*frames, overlay, patch, tps, merge, d_out_bf16, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200vit_gemm(const b200vit_gemm_args* args, b200vit_stream stream) {
+  if (!args) return fail(B200VIT_EINVAL, "gemm: null argument");
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_gemm(*args, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200vit_rmsnorm(const float* d_x, const float* d_w, void* d_out_bf16, int rows, int dim, float eps, b200vit_stream stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_rmsnorm(d_x, d_w, d_out_bf16, rows, dim, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200vit_attention(const void* d_qkv, void* d_out, const int32_t* h_cu_seqlens, int n_segments, int heads,
+                      b200vit_stream stream_) {
+  if (!d_qkv || !d_out || !h_cu_seqlens || n_segments < 0 || heads <= 0) return fail(B200VIT_EINVAL, "attention: bad argument");
+  int rc = check_arch();
+  if (rc) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  std::vector<int32_t> cu(h_cu_seqlens, h_cu_seqlens + n_segments + 1);
+  std::vector<AttnWork> work;
+  build_work(cu, work);
+  if (work.empty()) return 0;
+  AttnWork* d_work = nullptr;
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_work), work.size() * sizeof(AttnWork)));
+  B200_CUDA_OK(cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(AttnWork), cudaMemcpyHostToDevice, stream));
+  rc = launch_attention(d_qkv, d_out, d_work, static_cast<int>(work.size()), heads, stream);
+  cudaStreamSynchronize(stream);  // test entry point: the work list is freed before returning
+  cudaFree(d_work);
+  return rc;
+}
+
+int b200vit_cast_to_bf16(const void* d_in, int in_dtype, void* d_out, int64_t n, b200vit_stream stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_cast_bf16(d_in, in_dtype, d_out, n, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// Internal (C++) interfaces between the translation units of libb200vit.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/b200vit.h"
+
+namespace b200 {
+
+// thread-local error string behind b200vit_last_error()
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define B200_CUDA_OK(expr)                                  \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return ::b200::cuda_fail(_e, #expr); \
+  } while (0)
+
+int device_sm_count();
+int check_arch();  // 0 if the current device is sm_100, else B200VIT_EARCH
+
+// 2-D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], SWIZZLE_128B,
+// out-of-bounds elements read as zero.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
+
+// kernels (all enqueue on `stream`, no host sync)
+int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream);
+int launch_rmsnorm(const float* x, const float* w, void* out_bf16, int rows, int dim, float eps, cudaStream_t stream);
+int launch_cast_bf16(const void* in, int in_dtype, void* out, int64_t n, cudaStream_t stream);
+
+struct AttnWork {  // one CTA of the attention kernel: <= 64 query rows of one segment
+  int32_t q_start, q_len, kv_start, kv_len;
+};
+int launch_attention(const void* qkv, void* out, const AttnWork* d_work, int n_work, int heads, cudaStream_t stream);
+
+struct OverlayDev;  // device-side overlay description (overlay.cu)
+int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov, int patch, int tps, int merge,
+                            void* out_bf16, uint8_t* out_u8, cudaStream_t stream);
+
+}  // namespace b200

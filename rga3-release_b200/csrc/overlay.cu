@@ -1,0 +1,318 @@
+// STOM visual-prompt overlay + rescale/normalise + 2x14x14 patchify, one pass.
+//
+//   uint8 frames [T,H,W,3] (+ prompt layer, per-frame ops)  ->  bf16 [M, 3*tp*P*P]
+//
+// Integer-exact restatement of
+//   * Pillow alpha_composite on an opaque frame (the reference composites at
+//     /root/reference/model/STOM.py:84-87, :157-160, :204-207),
+//   * STOM.warp's forward scatter (:145-155) as a per-destination gather,
+//   * STOM.warp_point's cv2.circle stamp (:195-201),
+//   * PIL ImageDraw.rectangle outline (visual_prompt_generator.py:102-104),
+// followed by HF's fused rescale+normalise (image_processing_backends.py:291-331;
+// only 3x256 distinct values -> exact LUT) and the patchify permutation
+// (video_processing_qwen2_vl.py:255-272).  HBM-bound: 3 B/px frame + 0/1/4 B/px layer
+// in, 6 B/px out; every output element is written once with 16-byte stores.
+#include <cuda_bf16.h>
+
+#include <cstring>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int MAX_FRAMES_PER_LAUNCH = 128;
+
+struct FrameOpDev {
+  int32_t mode, sx, sy, cx, cy, r;
+  uint8_t zx, zy, pad0, pad1;
+  uint32_t rgba;  // little-endian r | g<<8 | b<<16 | a<<24
+};
+
+struct OverlayParams {
+  int32_t kind;
+  const uint8_t* layer;
+  int32_t box[4];
+  int32_t box_width;
+  int32_t circle_r;
+  uint32_t palette[256];
+  int16_t circle_hw[256];
+  FrameOpDev ops[MAX_FRAMES_PER_LAUNCH];
+};
+
+struct PatchParams {
+  const uint8_t* frames;
+  int32_t t, h, w;        // frames in this launch window, image size
+  int32_t t_total;        // frames in the clip (for the repeat-last-frame padding)
+  int32_t frame_base;     // index of ops[0] / first frame of this launch
+  int32_t patch, tps, merge, gh, gw;
+  int32_t cols;           // 3*tps*patch*patch
+  int64_t row_base;       // first output row of this launch
+  int64_t rows;           // rows produced by this launch
+};
+
+__constant__ uint16_t c_norm_lut[3 * 256];  // bf16 bits of (v - 255*mean_c) / (255*std_c)
+
+__device__ __forceinline__ uint32_t layer_at(const OverlayParams& ov, int h, int w, int y, int x) {
+  if (y < 0 || y >= h || x < 0 || x >= w) return 0u;
+  if (ov.kind == B200VIT_LAYER_RGBA) {
+    return __ldg(reinterpret_cast<const uint32_t*>(ov.layer) + static_cast<size_t>(y) * w + x);
+  } else if (ov.kind == B200VIT_LAYER_PALETTE) {
+    const uint8_t idx = __ldg(ov.layer + static_cast<size_t>(y) * w + x);
+    return idx ? ov.palette[idx] : 0u;
+  } else if (ov.kind == B200VIT_LAYER_BOX) {
+    // Pillow ImagingDrawRectangle, outline branch: rows t+i / b-i over [l..r]; columns r-i / l+i
+    // between rows t+width (included) and b-width+1 (excluded), either direction.
+    const int l = ov.box[0], t = ov.box[1], r = ov.box[2], b = ov.box[3], wd = ov.box_width;
+    const bool in_x = x >= min(l, r) && x <= max(l, r);
+    const bool rows = in_x && ((y >= t && y < t + wd) || (y <= b && y > b - wd));
+    const int ya = t + wd, yb = b - wd + 1;
+    const bool in_y = (ya < yb) ? (y >= ya && y < yb) : (ya > yb ? (y > yb && y <= ya) : false);
+    const bool cols = in_y && ((x <= r && x > r - wd) || (x >= l && x < l + wd));
+    return (rows || cols) ? ov.palette[1] : 0u;
+  }
+  return 0u;
+}
+
+// RGBA of the prompt layer as seen by destination pixel (y, x) of a frame; alpha 0 = untouched.
+__device__ __forceinline__ uint32_t overlay_at(const OverlayParams& ov, const FrameOpDev& op, int h, int w, int y, int x) {
+  if (op.mode == B200VIT_FRAME_LAYER) {
+    // candidates in row-major SOURCE order; the last one with alpha > 0 wins (STOM.py:149-154)
+    const int rb = y - op.sy, cb = x - op.sx;
+    const bool er = (y == 0) && op.zy, ec = (x == 0) && op.zx;
+    uint32_t v = layer_at(ov, h, w, rb, cb);
+    if ((v >> 24) == 0 && ec) v = layer_at(ov, h, w, rb, -1 - op.sx);
+    if ((v >> 24) == 0 && er) {
+      v = layer_at(ov, h, w, -1 - op.sy, cb);
+      if ((v >> 24) == 0 && ec) v = layer_at(ov, h, w, -1 - op.sy, -1 - op.sx);
+    }
+    return v;
+  } else if (op.mode == B200VIT_FRAME_CIRCLE) {
+    const int dy = y - op.cy;
+    if (dy < -op.r || dy > op.r) return 0u;
+    const int hw = ov.circle_hw[dy + op.r];
+    const int dx = x - op.cx;
+    return (hw >= 0 && dx >= -hw && dx <= hw) ? op.rgba : 0u;
+  }
+  return 0u;
+}
+
+// Pillow AlphaComposite.c with dst alpha = 255 (see oracle/overlay_ref.py)
+__device__ __forceinline__ uint32_t composite_ch(uint32_t d, uint32_t s, uint32_t a) {
+  const uint32_t t = s * (a * 128u) + d * ((255u - a) * 128u) + (0x80u << 7);
+  return (((t >> 8) + t) >> 8) >> 7;
+}
+
+template <bool HAS_OVERLAY>
+__global__ void __launch_bounds__(256)
+overlay_patchify_kernel(const __grid_constant__ PatchParams p, const __grid_constant__ OverlayParams ov,
+                        __nv_bfloat16* __restrict__ out) {
+  __shared__ uint16_t lut[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = c_norm_lut[i];
+  __syncthreads();
+  const int chunks = p.cols >> 3;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= p.rows * chunks) return;
+  const int64_t row = gid / chunks;
+  const int col0 = static_cast<int>(gid % chunks) * 8;
+  // row -> (t, bh, bw, mh, mw)
+  const int mm = p.merge * p.merge;
+  const int gw2 = p.gw / p.merge, gh2 = p.gh / p.merge;
+  const int64_t grow = row + p.row_base;
+  const int mi = static_cast<int>(grow % mm);
+  int64_t rest = grow / mm;
+  const int bw = static_cast<int>(rest % gw2);
+  rest /= gw2;
+  const int bh = static_cast<int>(rest % gh2);
+  const int tt = static_cast<int>(rest / gh2);
+  const int y0 = (bh * p.merge + mi / p.merge) * p.patch;
+  const int x0 = (bw * p.merge + mi % p.merge) * p.patch;
+  const int pp = p.patch * p.patch;
+  uint32_t packed[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = col0 + j;
+    const int c = col / (p.tps * pp);
+    const int r2 = col % (p.tps * pp);
+    const int tp = r2 / pp;
+    const int ph = (r2 % pp) / p.patch;
+    const int pw = r2 % p.patch;
+    int f = tt * p.tps + tp;
+    f = min(f, p.t_total - 1);  // odd T: repeat the last frame (HF videoproc :245-249)
+    const int y = y0 + ph, x = x0 + pw;
+    uint32_t d = __ldg(p.frames + ((static_cast<size_t>(f - p.frame_base) * p.h + y) * p.w + x) * 3 + c);
+    if (HAS_OVERLAY) {
+      const uint32_t s = overlay_at(ov, ov.ops[f - p.frame_base], p.h, p.w, y, x);
+      const uint32_t a = s >> 24;
+      if (a) d = composite_ch(d, (s >> (8 * c)) & 0xffu, a);
+    }
+    const uint32_t bits = lut[c * 256 + d];
+    if (j & 1)
+      packed[j >> 1] |= bits << 16;
+    else
+      packed[j >> 1] = bits;
+  }
+  *reinterpret_cast<uint4*>(out + row * p.cols + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+__global__ void __launch_bounds__(256)
+overlay_composite_kernel(const __grid_constant__ PatchParams p, const __grid_constant__ OverlayParams ov,
+                         uint8_t* __restrict__ out) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t npx = static_cast<int64_t>(p.t) * p.h * p.w;
+  if (gid >= npx) return;
+  const int x = static_cast<int>(gid % p.w);
+  const int y = static_cast<int>((gid / p.w) % p.h);
+  const int f = static_cast<int>(gid / (static_cast<int64_t>(p.w) * p.h));
+  const uint32_t s = overlay_at(ov, ov.ops[f], p.h, p.w, y, x);
+  const uint32_t a = s >> 24;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint32_t d = p.frames[gid * 3 + c];
+    if (a) d = composite_ch(d, (s >> (8 * c)) & 0xffu, a);
+    out[gid * 3 + c] = static_cast<uint8_t>(d);
+  }
+}
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return static_cast<uint16_t>(u >> 16);
+}
+
+int upload_lut() {
+  static bool done = false;
+  if (done) return 0;
+  // HF: mean_t = float32(mean) * 255, std_t = float32(std) * 255; (float(v) - mean_t) / std_t in fp32
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+  uint16_t lut[3 * 256];
+  for (int c = 0; c < 3; ++c) {
+    volatile float m = mean[c] * 255.0f;
+    volatile float s = stdv[c] * 255.0f;
+    for (int v = 0; v < 256; ++v) {
+      volatile float d = static_cast<float>(v) - m;
+      volatile float q = d / s;
+      lut[c * 256 + v] = f32_to_bf16_rne(q);
+    }
+  }
+  B200_CUDA_OK(cudaMemcpyToSymbol(c_norm_lut, lut, sizeof(lut)));
+  done = true;
+  return 0;
+}
+
+// OpenCV drawing.cpp Circle(): integer midpoint circle, filled -> per-row half widths.
+void circle_halfwidths(int r, int16_t* hw) {
+  for (int i = 0; i < 2 * r + 1; ++i) hw[i] = -1;
+  int err = 0, dx = r, dy = 0, plus = 1, minus = (r << 1) - 1;
+  while (dx >= dy) {
+    const int rows[2] = {dy, dx}, half[2] = {dx, dy};
+    for (int k = 0; k < 2; ++k)
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        const int i = r + sgn * rows[k];
+        if (half[k] > hw[i]) hw[i] = static_cast<int16_t>(half[k]);
+      }
+    dy++;
+    err += plus;
+    plus += 2;
+    const int mask = (err <= 0) - 1;
+    err -= minus & mask;
+    dx += mask;
+    minus -= mask & 2;
+  }
+}
+
+int fill_overlay(OverlayParams& o, const b200vit_overlay* ov, int f0, int nf, int t_total) {
+  std::memset(&o, 0, sizeof(o));
+  if (ov == nullptr) return 0;
+  o.kind = ov->kind;
+  o.layer = ov->d_layer;
+  if ((ov->kind == B200VIT_LAYER_RGBA || ov->kind == B200VIT_LAYER_PALETTE) && ov->d_layer == nullptr)
+    return fail(B200VIT_EINVAL, "overlay: layer kind needs d_layer");
+  if (ov->kind == B200VIT_LAYER_RGBA && (reinterpret_cast<uintptr_t>(ov->d_layer) & 3))
+    return fail(B200VIT_EALIGN, "overlay: RGBA layer must be 4-byte aligned");
+  for (int i = 0; i < 4; ++i) o.box[i] = ov->box[i];
+  o.box_width = ov->box_width < 1 ? 1 : ov->box_width;
+  for (int i = 0; i < 256; ++i)
+    o.palette[i] = ov->palette[i][0] | (ov->palette[i][1] << 8) | (ov->palette[i][2] << 16) |
+                   (static_cast<uint32_t>(ov->palette[i][3]) << 24);
+  o.circle_r = -1;
+  for (int i = 0; i < nf; ++i) {
+    FrameOpDev& d = o.ops[i];
+    if (ov->h_ops == nullptr || f0 + i >= t_total) {
+      d.mode = B200VIT_FRAME_NONE;
+      continue;
+    }
+    const b200vit_frame_op& s = ov->h_ops[f0 + i];
+    d.mode = s.mode, d.sx = s.sx, d.sy = s.sy, d.cx = s.cx, d.cy = s.cy, d.r = s.r;
+    d.zx = s.zx ? 1 : 0, d.zy = s.zy ? 1 : 0;
+    d.rgba = s.rgba[0] | (s.rgba[1] << 8) | (s.rgba[2] << 16) | (static_cast<uint32_t>(s.rgba[3]) << 24);
+    if (s.mode == B200VIT_FRAME_CIRCLE) {
+      if (s.r < 0 || s.r > 127) return fail(B200VIT_EINVAL, "overlay: circle radius must be in [0,127]");
+      if (o.circle_r >= 0 && o.circle_r != s.r)
+        return fail(B200VIT_EINVAL, "overlay: all circle stamps of a clip share one radius (min(h,w)//20)");
+      o.circle_r = s.r;
+    } else if (s.mode == B200VIT_FRAME_LAYER && ov->kind == B200VIT_LAYER_NONE) {
+      return fail(B200VIT_EINVAL, "overlay: frame op uses the layer but kind is NONE");
+    } else if (s.mode < 0 || s.mode > 2) {
+      return fail(B200VIT_EINVAL, "overlay: unknown frame mode");
+    }
+  }
+  if (o.circle_r >= 0) circle_halfwidths(o.circle_r, o.circle_hw);
+  return 0;
+}
+
+}  // namespace
+
+// out_bf16 != nullptr: patchified bf16 matrix; out_u8 != nullptr: composited frames.
+int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov, int patch, int tps, int merge,
+                            void* out_bf16, uint8_t* out_u8, cudaStream_t stream) {
+  if (fr.d_frames == nullptr || fr.t <= 0 || fr.h <= 0 || fr.w <= 0) return fail(B200VIT_EINVAL, "frames: empty clip");
+  const int unit = patch * merge;
+  if (out_bf16 && (fr.h % unit || fr.w % unit))
+    return fail(B200VIT_EINVAL, "frames: H and W must be multiples of patch*merge (resize is out of scope)");
+  const int cols = 3 * tps * patch * patch;
+  if (out_bf16 && cols % 8) return fail(B200VIT_EINVAL, "patchify: 3*tps*patch^2 must be a multiple of 8");
+  if (out_bf16 && (reinterpret_cast<uintptr_t>(out_bf16) & 15)) return fail(B200VIT_EALIGN, "patchify: out must be 16-byte aligned");
+  int rc = upload_lut();
+  if (rc) return rc;
+  const int gh = fr.h / patch, gw = fr.w / patch;
+  const int t_pad = (fr.t + tps - 1) / tps * tps;
+  // frames are processed in windows of whole temporal patches so per-frame ops fit the kernel parameters
+  const int win = MAX_FRAMES_PER_LAUNCH / tps * tps;
+  for (int f0 = 0; f0 < t_pad; f0 += win) {
+    const int nf_pad = (t_pad - f0 < win) ? (t_pad - f0) : win;      // padded frames covered
+    const int nf = (fr.t - f0 < nf_pad) ? (fr.t - f0) : nf_pad;      // real frames available
+    OverlayParams o;
+    rc = fill_overlay(o, ov, f0, nf, fr.t);
+    if (rc) return rc;
+    PatchParams p;
+    p.frames = fr.d_frames + static_cast<size_t>(f0) * fr.h * fr.w * 3;
+    p.t = nf, p.h = fr.h, p.w = fr.w, p.t_total = fr.t, p.frame_base = f0;
+    p.patch = patch, p.tps = tps, p.merge = merge, p.gh = gh, p.gw = gw, p.cols = cols;
+    p.row_base = static_cast<int64_t>(f0 / tps) * gh * gw;
+    p.rows = static_cast<int64_t>(nf_pad / tps) * gh * gw;
+    if (out_bf16) {
+      const int64_t threads = p.rows * (cols / 8);
+      const int grid = static_cast<int>((threads + 255) / 256);
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_bf16) + p.row_base * cols;
+      if (ov != nullptr && ov->h_ops != nullptr)
+        overlay_patchify_kernel<true><<<grid, 256, 0, stream>>>(p, o, dst);
+      else
+        overlay_patchify_kernel<false><<<grid, 256, 0, stream>>>(p, o, dst);
+    }
+    if (out_u8) {
+      const int64_t npx = static_cast<int64_t>(nf) * fr.h * fr.w;
+      const int grid = static_cast<int>((npx + 255) / 256);
+      p.frame_base = 0;
+      overlay_composite_kernel<<<grid, 256, 0, stream>>>(p, o, out_u8 + static_cast<size_t>(f0) * fr.h * fr.w * 3);
+    }
+    B200_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace b200

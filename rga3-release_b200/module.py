@@ -1,0 +1,326 @@
+"""Drop-in replacement for HF ``Qwen2_5_VisionTransformerPretrainedModel`` backed by
+libb200vit.so.
+
+Same constructor config, same ``state_dict`` keys/shapes, same call signature
+``forward(hidden_states [M,1176], grid_thw [n,3]) -> merged embeddings`` as the
+module the reference calls at /root/reference/model/qwen_2_5_vl_sam2.py:182-200
+(through HF ``get_video_features``, modeling_qwen2_5_vl.py:1137-1177), plus the
+fused entry ``forward_frames`` that starts from uint8 frames and a STOM overlay.
+
+PyTorch is used for device memory, streams and (optional) CUDA-graph capture only;
+all arithmetic runs in the hand-written sm_100a kernels.  There is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .overlay import OverlaySpec
+
+
+class _Holder(nn.Module):
+    """Parameter holder with the HF names (weight / bias)."""
+
+    def __init__(self, w_shape, bias: bool, dtype, device, ones: bool = False):
+        super().__init__()
+        init = torch.ones if ones else torch.zeros
+        self.weight = nn.Parameter(init(w_shape, dtype=dtype, device=device), requires_grad=False)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(w_shape[0], dtype=dtype, device=device), requires_grad=False)
+
+
+class _Plan:
+    """Owns one b200vit_plan plus its workspace / static buffers."""
+
+    def __init__(self, grid: Tuple[Tuple[int, int, int], ...], cfg_c, device):
+        self.grid = grid
+        arr = (C.c_int64 * (3 * len(grid)))(*[v for g in grid for v in g])
+        handle = C.c_void_p()
+        _lib.check(_lib.lib().b200vit_plan_create(arr, len(grid), C.byref(cfg_c), C.byref(handle)), "plan_create")
+        self.handle = handle
+        self.m = int(sum(t * h * w for t, h, w in grid))
+        self.ws_bytes = int(_lib.lib().b200vit_workspace_bytes(handle))
+        self.workspace = None
+        self.device = device
+        self.graphs: Dict[str, tuple] = {}
+
+    def ensure_workspace(self):
+        if self.workspace is None:
+            self.workspace = torch.empty(self.ws_bytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 1024
+            self.ws_ptr = self.workspace.data_ptr() + off
+        return self.ws_ptr
+
+    def get(self, which: int, dtype) -> np.ndarray:
+        n = int(_lib.lib().b200vit_plan_get(self.handle, which, None, 0))
+        out = np.empty(n // np.dtype(dtype).itemsize, dtype=dtype)
+        _lib.lib().b200vit_plan_get(self.handle, which, out.ctypes.data_as(C.c_void_p), n)
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().b200vit_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _Output:
+    """Minimal stand-in for transformers' BaseModelOutputWithPooling (5.x return style)."""
+
+    def __init__(self, pooler_output, last_hidden_state=None):
+        self.pooler_output = pooler_output
+        self.last_hidden_state = last_hidden_state
+
+    def __getitem__(self, i):
+        return (self.last_hidden_state, self.pooler_output)[i]
+
+
+class B200VisionTower(nn.Module):
+    def __init__(self, config, device="cuda", dtype=torch.bfloat16, return_dict: Optional[bool] = None,
+                 use_cuda_graph: bool = False, output_fp32: bool = False):
+        super().__init__()
+        g = (lambda k, d=None: getattr(config, k, d)) if not isinstance(config, dict) else (lambda k, d=None: config.get(k, d))
+        self.config = config
+        self.depth = g("depth", 32)
+        self.hidden_size = g("hidden_size", 1280)
+        self.intermediate_size = g("intermediate_size", 3420)
+        self.num_heads = g("num_heads", 16)
+        self.out_hidden_size = g("out_hidden_size", 3584)
+        self.patch_size = g("patch_size", 14)
+        self.temporal_patch_size = g("temporal_patch_size", 2)
+        self.spatial_merge_size = g("spatial_merge_size", 2)
+        self.spatial_merge_unit = self.spatial_merge_size ** 2
+        self.window_size = g("window_size", 112)
+        self.in_channels = g("in_channels", 3)
+        self.fullatt_block_indexes = list(g("fullatt_block_indexes", [7, 15, 23, 31]))
+        if g("hidden_act", "silu") != "silu":
+            raise ValueError("only the SiLU-gated MLP of Qwen2.5-VL is implemented")
+        self._dtype = dtype
+        self._device = torch.device(device)
+        self.use_cuda_graph = use_cuda_graph
+        self.output_fp32 = output_fp32
+        if return_dict is None:  # transformers >= 5 returns an object with .pooler_output, 4.49 a tensor
+            try:
+                import transformers
+                return_dict = int(transformers.__version__.split(".")[0]) >= 5
+            except Exception:
+                return_dict = False
+        self.return_dict = return_dict
+
+        d, i, o, u = self.hidden_size, self.intermediate_size, self.out_hidden_size, self.spatial_merge_unit
+        mk = lambda shape, bias, ones=False: _Holder(shape, bias, dtype, self._device, ones)
+        self.patch_embed = nn.Module()
+        self.patch_embed.proj = mk((d, self.in_channels, self.temporal_patch_size, self.patch_size, self.patch_size), False)
+        self.blocks = nn.ModuleList()
+        for _ in range(self.depth):
+            b = nn.Module()
+            b.norm1, b.norm2 = mk((d,), False, True), mk((d,), False, True)
+            b.attn = nn.Module()
+            b.attn.qkv, b.attn.proj = mk((3 * d, d), True), mk((d, d), True)
+            b.mlp = nn.Module()
+            b.mlp.gate_proj, b.mlp.up_proj, b.mlp.down_proj = mk((i, d), True), mk((i, d), True), mk((d, i), True)
+            self.blocks.append(b)
+        self.merger = nn.Module()
+        self.merger.ln_q = mk((d,), False, True)
+        self.merger.mlp = nn.ModuleDict({"0": mk((u * d, u * d), True), "2": mk((o, u * d), True)})
+
+        self._cfg_c = _lib.Cfg()
+        for k, v in dict(depth=self.depth, hidden=d, intermediate=i, heads=self.num_heads, out_hidden=o,
+                         patch=self.patch_size, temporal_patch=self.temporal_patch_size, merge=self.spatial_merge_size,
+                         window=self.window_size, in_channels=self.in_channels,
+                         n_fullatt=len(self.fullatt_block_indexes)).items():
+            setattr(self._cfg_c, k, int(v))
+        for j, v in enumerate(self.fullatt_block_indexes):
+            self._cfg_c.fullatt[j] = int(v)
+        self._packed = None
+        self._plans: Dict[tuple, _Plan] = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    # ---- HF-style attributes
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def device(self):
+        return self._device
+
+    def _invalidate(self):
+        self._packed = None
+
+    @classmethod
+    def from_hf(cls, hf_tower, **kw):
+        """Build from an instantiated HF tower (copies its weights)."""
+        dev = kw.pop("device", "cuda")
+        m = cls(hf_tower.config, device=dev, **kw)
+        sd = {k: v for k, v in hf_tower.state_dict().items() if "inv_freq" not in k}
+        m.load_state_dict(sd)
+        return m
+
+    # ---- weight packing (once): bf16 [N,K] matrices, gate/up interleave, I -> Ipad zero pad
+    @torch.no_grad()
+    def pack_weights(self):
+        d, i = self.hidden_size, self.intermediate_size
+        ipad = (i + 127) // 128 * 128
+        dev = self._device
+        keep = []
+
+        def bf(t):
+            t = t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def f32(t):
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        layers = (_lib.LayerWeights * self.depth)()
+        for li, b in enumerate(self.blocks):
+            lw = layers[li]
+            lw.norm1_w, lw.norm2_w = f32(b.norm1.weight), f32(b.norm2.weight)
+            lw.qkv_w, lw.qkv_b = bf(b.attn.qkv.weight), f32(b.attn.qkv.bias)
+            lw.proj_w, lw.proj_b = bf(b.attn.proj.weight), f32(b.attn.proj.bias)
+            gw = torch.zeros(ipad, 2, d, dtype=torch.float32, device=dev)
+            gw[:i, 0] = b.mlp.gate_proj.weight.float()
+            gw[:i, 1] = b.mlp.up_proj.weight.float()
+            gb = torch.zeros(ipad, 2, dtype=torch.float32, device=dev)
+            gb[:i, 0] = b.mlp.gate_proj.bias.float()
+            gb[:i, 1] = b.mlp.up_proj.bias.float()
+            lw.gateup_w, lw.gateup_b = bf(gw.view(2 * ipad, d)), f32(gb.view(2 * ipad))
+            dw = torch.zeros(d, ipad, dtype=torch.float32, device=dev)
+            dw[:, :i] = b.mlp.down_proj.weight.float()
+            lw.down_w, lw.down_b = bf(dw), f32(b.mlp.down_proj.bias)
+        w = _lib.Weights()
+        w.patch_w = bf(self.patch_embed.proj.weight.reshape(d, -1))
+        w.layers = layers
+        w.merger_ln_w = f32(self.merger.ln_q.weight)
+        w.merger_fc1_w, w.merger_fc1_b = bf(self.merger.mlp["0"].weight), f32(self.merger.mlp["0"].bias)
+        w.merger_fc2_w, w.merger_fc2_b = bf(self.merger.mlp["2"].weight), f32(self.merger.mlp["2"].bias)
+        w.ipad = ipad
+        self._packed = (w, layers, keep)
+        return w
+
+    def _weights(self):
+        if self._packed is None:
+            self.pack_weights()
+        return self._packed[0]
+
+    # ---- plans
+    def plan_for(self, grid_thw) -> _Plan:
+        if isinstance(grid_thw, torch.Tensor):
+            grid = tuple(tuple(int(v) for v in row) for row in grid_thw.detach().cpu().tolist())
+        else:
+            grid = tuple(tuple(int(v) for v in row) for row in np.asarray(grid_thw).reshape(-1, 3).tolist())
+        p = self._plans.get(grid)
+        if p is None:
+            p = _Plan(grid, self._cfg_c, self._device)
+            self._plans[grid] = p
+        return p
+
+    # ---- the hot path
+    def _run(self, plan: _Plan, pixel_values, frames_c, overlay_c, out, last_hidden):
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        rc = _lib.lib().b200vit_forward(
+            plan.handle, C.byref(self._weights()),
+            pixel_values.data_ptr() if pixel_values is not None else None,
+            C.byref(frames_c) if frames_c is not None else None,
+            C.byref(overlay_c) if overlay_c is not None else None,
+            out.data_ptr(), 1 if out.dtype == torch.float32 else 0,
+            last_hidden.data_ptr() if last_hidden is not None else None,
+            plan.ensure_workspace(), plan.ws_bytes, stream)
+        _lib.check(rc, "b200vit_forward")
+
+    def _wrap(self, out, last_hidden):
+        if self.return_dict:
+            return _Output(out, last_hidden)
+        return out
+
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, grid_thw, output_last_hidden_state: bool = False, **kwargs):
+        """hidden_states: [M, C*tp*p*p] float (bf16/fp16/fp32), CUDA; grid_thw: [n,3]."""
+        if not hidden_states.is_cuda:
+            raise ValueError("B200VisionTower.forward: hidden_states must be a CUDA tensor (no CPU path)")
+        plan = self.plan_for(grid_thw)
+        kpe = self.in_channels * self.temporal_patch_size * self.patch_size ** 2
+        if hidden_states.dim() != 2 or hidden_states.shape[0] != plan.m or hidden_states.shape[1] != kpe:
+            raise ValueError(f"hidden_states must be [{plan.m}, {kpe}] for grid_thw {plan.grid}, got {tuple(hidden_states.shape)}")
+        x = hidden_states.contiguous()
+        if x.dtype != torch.bfloat16:
+            code = {torch.float32: 0, torch.float16: 1}.get(x.dtype)
+            if code is None:
+                raise ValueError(f"unsupported pixel dtype {x.dtype}")
+            xb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _lib.check(_lib.lib().b200vit_cast_to_bf16(x.data_ptr(), code, xb.data_ptr(), x.numel(), stream), "cast")
+            x = xb
+        out_dtype = torch.float32 if self.output_fp32 else self._dtype
+        if self.use_cuda_graph and not output_last_hidden_state:
+            return self._wrap(self._graph_forward(plan, x, out_dtype), None)
+        out = torch.empty(plan.m // self.spatial_merge_unit, self.out_hidden_size, dtype=out_dtype, device=x.device)
+        last = torch.empty(plan.m, self.hidden_size, dtype=torch.float32, device=x.device) if output_last_hidden_state else None
+        self._run(plan, x, None, None, out, last)
+        return self._wrap(out, last)
+
+    def _graph_forward(self, plan: _Plan, x, out_dtype):
+        key = f"pv-{out_dtype}"
+        g = plan.graphs.get(key)
+        if g is None:
+            static_in = torch.empty_like(x)
+            static_out = torch.empty(plan.m // self.spatial_merge_unit, self.out_hidden_size, dtype=out_dtype, device=x.device)
+            static_in.copy_(x)
+            s = torch.cuda.Stream(self._device)
+            s.wait_stream(torch.cuda.current_stream(self._device))
+            with torch.cuda.stream(s):
+                for _ in range(2):  # warm-up outside capture: lazy uploads, func attributes
+                    self._run(plan, static_in, None, None, static_out, None)
+            torch.cuda.current_stream(self._device).wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._run(plan, static_in, None, None, static_out, None)
+            g = (graph, static_in, static_out)
+            plan.graphs[key] = g
+        graph, static_in, static_out = g
+        static_in.copy_(x)
+        graph.replay()
+        return static_out
+
+    @torch.no_grad()
+    def forward_frames(self, frames_u8: torch.Tensor, overlay: Optional[OverlaySpec] = None, grid_thw=None):
+        """Fused entry: uint8 frames [T,H,W,3] (CUDA) + optional STOM overlay -> merged embeddings.
+        Equivalent to PIL overlay -> Qwen2VLVideoProcessor(do_resize=False) -> tower."""
+        if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
+            raise ValueError("frames must be a CUDA uint8 tensor [T,H,W,3]")
+        t, h, w, _ = frames_u8.shape
+        if grid_thw is None:
+            tps = self.temporal_patch_size
+            grid_thw = [[(t + tps - 1) // tps, h // self.patch_size, w // self.patch_size]]
+        plan = self.plan_for(grid_thw)
+        fr = frames_u8.contiguous()
+        fc = _lib.Frames(fr.data_ptr(), t, h, w)
+        oc = overlay.to_c(t) if overlay is not None else None
+        out_dtype = torch.float32 if self.output_fp32 else self._dtype
+        out = torch.empty(plan.m // self.spatial_merge_unit, self.out_hidden_size, dtype=out_dtype, device=fr.device)
+        self._run(plan, None, fc, oc, out, None)
+        return self._wrap(out, None)
+
+    def launches_per_forward(self, grid_thw, with_frames=False) -> int:
+        return int(_lib.lib().b200vit_forward_launches(self.plan_for(grid_thw).handle, 1 if with_frames else 0))
+
+
+def install(model, **kw):
+    """Swap the HF vision tower inside a Qwen2.5-VL / UniGR model for the B200 one.
+    Handles both attribute layouts: ``model.model.visual`` (transformers 5.x) and
+    ``model.visual`` (4.49, used by /root/reference/train_joint.py:190)."""
+    holder = model.model if hasattr(getattr(model, "model", None), "visual") else model
+    hf_tower = holder.visual
+    tower = B200VisionTower.from_hf(hf_tower, device=next(hf_tower.parameters()).device, **kw)
+    holder.visual = tower
+    return tower

@@ -1,0 +1,267 @@
+"""Per-kernel parity on the B200: every CUDA kernel, called through the C ABI,
+against the CPU oracle / an fp32 restatement on the same seeded inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import rga3_release_b200 as vit
+from rga3_release_b200 import _lib
+from oracle import overlay_ref, patchify_ref, tower_ref
+
+DEV = "cuda"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def run_gemm(a, b, epi, out, bias=None, row_map=None, cos=None, sin=None, ldo=None, rope_cols=0):
+    g = _lib.GemmArgs()
+    g.d_a, g.d_b, g.d_out = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.d_bias = bias.data_ptr() if bias is not None else None
+    g.d_row_map = row_map.data_ptr() if row_map is not None else None
+    g.d_cos = cos.data_ptr() if cos is not None else None
+    g.d_sin = sin.data_ptr() if sin is not None else None
+    g.m, g.k = a.shape
+    g.n = b.shape[0]
+    g.ldo = ldo if ldo is not None else out.shape[1]
+    g.rope_cols = rope_cols
+    g.epilogue = epi
+    _lib.check(_lib.lib().b200vit_gemm(C.byref(g), _stream()), "gemm")
+    torch.cuda.synchronize()
+
+
+def rnd(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def close(out, ref, tol=2e-2):
+    out, ref = out.float().cpu(), ref.float().cpu()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    assert err <= tol * scale, f"max err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 160, 1176), (1000, 1280, 160), (4096, 1280, 1280), (77, 512, 3456)])
+def test_gemm_store_f32_rowmap(m, n, k):
+    a, b = rnd((m, k), 1), rnd((n, k), 2, 0.05)
+    perm = torch.randperm(m, generator=torch.Generator().manual_seed(3)).to(torch.int32).to(DEV)
+    out = torch.zeros(m, n, dtype=torch.float32, device=DEV)
+    run_gemm(a, b, _lib.EPI_STORE_F32, out, row_map=perm)
+    ref = torch.empty_like(out)
+    ref[perm.long()] = a.float() @ b.float().t()
+    close(out, ref, 1e-3)
+
+
+def test_gemm_exact_small_integers():
+    # integer-valued bf16 inputs: fp32 accumulation is exact, so the result must be bit-exact
+    g = torch.Generator().manual_seed(0)
+    a = torch.randint(-4, 5, (256, 1280), generator=g).to(torch.bfloat16).to(DEV)
+    b = torch.randint(-4, 5, (512, 1280), generator=g).to(torch.bfloat16).to(DEV)
+    out = torch.zeros(256, 512, dtype=torch.float32, device=DEV)
+    run_gemm(a, b, _lib.EPI_STORE_F32, out)
+    assert torch.equal(out, a.float() @ b.float().t())
+
+
+@pytest.mark.parametrize("m,d", [(200, 160), (1024, 1280)])
+def test_gemm_qkv_rope(m, d):
+    nh = d // 80
+    a, b = rnd((m, d), 4), rnd((3 * d, d), 5, 0.05)
+    bias = rnd((3 * d,), 6, 0.1, torch.float32)
+    ang = rnd((m, 40), 7, 3.0, torch.float32)
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    out = torch.zeros(m, 3 * d, dtype=torch.bfloat16, device=DEV)
+    run_gemm(a, b, _lib.EPI_QKV_ROPE, out, bias=bias, cos=cos, sin=sin, rope_cols=2 * d)
+    qkv = (a.float() @ b.float().t() + bias).cpu().reshape(m, 3, nh, 80)
+    c80 = torch.cat([cos, cos], -1).cpu()
+    s80 = torch.cat([sin, sin], -1).cpu()
+    q, k = tower_ref.rope_ref(qkv[:, 0], qkv[:, 1], c80, s80)
+    ref = torch.stack([q, k, qkv[:, 2]], 1).reshape(m, 3 * d)
+    close(out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 160, 256), (2048, 1280, 3456)])
+def test_gemm_bias_residual(m, n, k):
+    a, b = rnd((m, k), 8), rnd((n, k), 9, 0.05)
+    bias = rnd((n,), 10, 0.1, torch.float32)
+    x0 = rnd((m, n), 11, 1.0, torch.float32)
+    x = x0.clone()
+    run_gemm(a, b, _lib.EPI_BIAS_RESIDUAL, x, bias=bias)
+    close(x, x0 + a.float() @ b.float().t() + bias, 1e-3)
+
+
+@pytest.mark.parametrize("m,ipad,k", [(300, 256, 160), (1024, 3456, 1280)])
+def test_gemm_swiglu(m, ipad, k):
+    a, b = rnd((m, k), 12), rnd((2 * ipad, k), 13, 0.05)
+    bias = rnd((2 * ipad,), 14, 0.1, torch.float32)
+    out = torch.zeros(m, ipad, dtype=torch.bfloat16, device=DEV)
+    run_gemm(a, b, _lib.EPI_SWIGLU, out, bias=bias, ldo=ipad)
+    z = a.float() @ b.float().t() + bias
+    ref = torch.nn.functional.silu(z[:, 0::2]) * z[:, 1::2]
+    close(out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("epi", ["gelu", "bf16", "f32"])
+def test_gemm_bias_epilogues(epi):
+    m, n, k = 520, 640, 640
+    a, b = rnd((m, k), 15), rnd((n, k), 16, 0.05)
+    bias = rnd((n,), 17, 0.1, torch.float32)
+    z = a.float() @ b.float().t() + bias
+    if epi == "gelu":
+        out = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+        run_gemm(a, b, _lib.EPI_BIAS_GELU, out, bias=bias)
+        close(out, torch.nn.functional.gelu(z), 1e-2)
+    else:
+        perm = torch.randperm(m, generator=torch.Generator().manual_seed(18)).to(torch.int32).to(DEV)
+        dt = torch.bfloat16 if epi == "bf16" else torch.float32
+        out = torch.zeros(m, n, dtype=dt, device=DEV)
+        run_gemm(a, b, _lib.EPI_BIAS_BF16 if epi == "bf16" else _lib.EPI_BIAS_F32, out, bias=bias, row_map=perm)
+        ref = torch.empty_like(z)
+        ref[perm.long()] = z
+        close(out, ref, 1e-2 if epi == "bf16" else 1e-3)
+
+
+def test_gemm_rejects_bad_args():
+    a, b = rnd((64, 60), 1), rnd((64, 60), 2)   # K % 8 != 0
+    out = torch.zeros(64, 64, dtype=torch.float32, device=DEV)
+    with pytest.raises(ValueError):
+        run_gemm(a, b, _lib.EPI_STORE_F32, out)
+
+
+@pytest.mark.parametrize("rows,dim", [(1000, 1280), (37, 160), (16, 5120)])
+def test_rmsnorm(rows, dim):
+    x = rnd((rows, dim), 20, 2.0, torch.float32)
+    w = (1 + 0.1 * rnd((dim,), 21, 1.0, torch.float32))
+    out = torch.zeros(rows, dim, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().b200vit_rmsnorm(x.data_ptr(), w.data_ptr(), out.data_ptr(), rows, dim, 1e-6, _stream()), "rmsnorm")
+    torch.cuda.synchronize()
+    close(out, tower_ref.rmsnorm_ref(x.cpu(), w.cpu()), 1e-2)
+
+
+@pytest.mark.parametrize("lens,heads", [([64, 64, 32, 16, 64], 2), ([1024, 1024], 4), ([100, 7, 2304, 64, 1], 2), ([60], 16)])
+def test_attention_varlen(lens, heads):
+    m, d = sum(lens), heads * 80
+    qkv = rnd((m, 3 * d), 30, 1.0)
+    out = torch.zeros(m, d, dtype=torch.bfloat16, device=DEV)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    _lib.check(_lib.lib().b200vit_attention(qkv.data_ptr(), out.data_ptr(), cu.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            len(lens), heads, _stream()), "attention")
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().cpu().reshape(m, 3, heads, 80).unbind(1)
+    ref = tower_ref.varlen_attention_ref(q, k, v, cu, 80 ** -0.5)
+    close(out, ref, 1e-2)
+
+
+def test_attention_empty_segment_list():
+    qkv = rnd((64, 3 * 160), 31)
+    out = torch.zeros(64, 160, dtype=torch.bfloat16, device=DEV)
+    cu = np.zeros(1, dtype=np.int32)
+    assert _lib.lib().b200vit_attention(qkv.data_ptr(), out.data_ptr(), cu.ctypes.data_as(C.POINTER(C.c_int32)), 0, 2, _stream()) == 0
+
+
+def test_cast_to_bf16():
+    x = rnd((1000, 1176), 40, 1.0, torch.float32)
+    out = torch.zeros(1000, 1176, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().b200vit_cast_to_bf16(x.data_ptr(), 0, out.data_ptr(), x.numel(), _stream()), "cast")
+    torch.cuda.synchronize()
+    assert torch.equal(out, x.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------ overlay + patchify (bit-exact)
+def _clip(t, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (t, h, w, 3), dtype=torch.uint8, generator=g)
+
+
+def _layer(h, w):
+    from PIL import Image, ImageDraw
+    vip = Image.new("RGBA", (w, h), (0, 0, 0, 0))
+    d = ImageDraw.Draw(vip)
+    d.ellipse([(w // 3, h // 4), (2 * w // 3, 3 * h // 4)], fill=(0, 255, 0, 100))
+    d.rectangle([(w // 8, h // 7), (7 * w // 8, 6 * h // 7)], outline=(255, 0, 0, 200), width=3)
+    return np.array(vip)
+
+
+def _ops_for(t, h, w):
+    flows = [(0.0, 0.0), (3.0, -2.0), (-4.7, 5.2), (-0.7, -0.4), (40.5, 10.25), (-900.0, 3.0)]
+    ops, ref_ops = [], []
+    for i in range(t):
+        if i % 4 == 3:
+            o = vit.FrameOp(mode=_lib.FRAME_CIRCLE, cx=w // 2 + i, cy=h // 3 - i, r=min(h, w) // 20, rgba=(9, 200, 30, 120))
+            ref_ops.append(dict(mode=2, cx=o.cx, cy=o.cy, r=o.r, rgba=o.rgba))
+        elif i % 4 == 2 and i > 4:
+            o = vit.FrameOp()
+            ref_ops.append(dict(mode=0))
+        else:
+            fx, fy = flows[i % len(flows)]
+            sx, zx = vit.shift_from_flow(fx, w)
+            sy, zy = vit.shift_from_flow(fy, h)
+            o = vit.FrameOp(mode=_lib.FRAME_LAYER, sx=sx, sy=sy, zx=zx, zy=zy)
+            ref_ops.append(dict(mode=1, sx=sx, zx=zx, sy=sy, zy=zy))
+        ops.append(o)
+    return ops, ref_ops
+
+
+@pytest.mark.parametrize("t,h,w", [(6, 56, 84), (5, 28, 56)])
+def test_overlay_composite_and_patchify_bitexact(t, h, w):
+    frames = _clip(t, h, w, 50)
+    layer = _layer(h, w)
+    ops, ref_ops = _ops_for(t, h, w)
+    spec = vit.OverlaySpec.from_rgba(layer, ops)
+    fr = frames.to(DEV)
+    fc = _lib.Frames(fr.data_ptr(), t, h, w)
+    oc = spec.to_c(t)
+    comp = torch.zeros_like(fr)
+    _lib.check(_lib.lib().b200vit_overlay_composite(C.byref(fc), C.byref(oc), comp.data_ptr(), _stream()), "composite")
+    torch.cuda.synchronize()
+    ref = overlay_ref.overlay_clip_ref(frames.numpy(), layer, ref_ops)
+    assert np.array_equal(comp.cpu().numpy(), ref)
+    pv_ref, grid = patchify_ref.patchify_ref(ref)
+    out = torch.zeros(pv_ref.shape, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().b200vit_overlay_patchify(C.byref(fc), C.byref(oc), 14, 2, 2, out.data_ptr(), _stream()), "patchify")
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), torch.from_numpy(pv_ref).to(torch.bfloat16))
+
+
+def test_overlay_palette_and_box_kinds():
+    t, h, w = 4, 56, 56
+    frames = _clip(t, h, w, 51)
+    fr = frames.to(DEV)
+    fc = _lib.Frames(fr.data_ptr(), t, h, w)
+    ops = [vit.FrameOp(mode=_lib.FRAME_LAYER, sx=i, sy=-i) for i in range(t)]
+    ref_ops = [dict(mode=1, sx=i, sy=-i) for i in range(t)]
+    # palette: two colours
+    idx = np.zeros((h, w), np.uint8)
+    idx[10:30, 5:25] = 1
+    idx[20:50, 20:40] = 2
+    pal = [(0, 0, 0, 0), (255, 0, 0, 200), (0, 0, 255, 90)]
+    lay = np.zeros((h, w, 4), np.uint8)
+    lay[idx == 1] = pal[1]
+    lay[idx == 2] = pal[2]
+    for spec, lay_ref in ((vit.OverlaySpec.from_palette(idx, pal, ops), lay),
+                          (vit.OverlaySpec.from_box((8, 6, 40, 50), 4, (0, 255, 0, 210), ops),
+                           overlay_ref.box_layer_ref(h, w, (8, 6, 40, 50), 4, (0, 255, 0, 210))),
+                          (vit.OverlaySpec.from_box((13, 4, 14, 13), 5, (0, 255, 0, 210), ops),
+                           overlay_ref.box_layer_ref(h, w, (13, 4, 14, 13), 5, (0, 255, 0, 210)))):
+        oc = spec.to_c(t)
+        comp = torch.zeros_like(fr)
+        _lib.check(_lib.lib().b200vit_overlay_composite(C.byref(fc), C.byref(oc), comp.data_ptr(), _stream()), "composite")
+        torch.cuda.synchronize()
+        assert np.array_equal(comp.cpu().numpy(), overlay_ref.overlay_clip_ref(frames.numpy(), lay_ref, ref_ops))
+
+
+def test_patchify_golden_fixture(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, "patchify_hf.npz"))
+    fr = torch.from_numpy(z["frames"]).to(DEV)
+    t, h, w, _ = fr.shape
+    fc = _lib.Frames(fr.data_ptr(), t, h, w)
+    out = torch.zeros(z["pixel_values"].shape, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().b200vit_overlay_patchify(C.byref(fc), None, 14, 2, 2, out.data_ptr(), _stream()), "patchify")
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), torch.from_numpy(z["pixel_values"]).to(torch.bfloat16))

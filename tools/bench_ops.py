@@ -1,0 +1,112 @@
+"""Per-kernel timing at the config-2 shapes (M = 8192): CUDA events, L2 flushed between
+iterations.  Development aid; bench.py is the judged number."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rga3_release_b200 as vit
+from rga3_release_b200 import _lib
+
+DEV = "cuda"
+M = int(os.environ.get("M", 8192))
+D, I, IPAD = 1280, 3420, 3456
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def timeit(fn, iters=20, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def gemm_fn(m, n, k, epi, ldo=None, rope=False, out_dtype=torch.bfloat16):
+    a = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+    b = (torch.randn(n, k, device=DEV) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(n, device=DEV)
+    ocols = ldo if ldo else n
+    out = torch.zeros(m, ocols, dtype=out_dtype, device=DEV)
+    cos = torch.rand(m, 40, device=DEV)
+    sin = torch.rand(m, 40, device=DEV)
+    g = _lib.GemmArgs()
+    g.d_a, g.d_b, g.d_out, g.d_bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr()
+    g.d_cos, g.d_sin = cos.data_ptr(), sin.data_ptr()
+    g.m, g.n, g.k, g.ldo, g.rope_cols, g.epilogue = m, n, k, ocols, (2 * n // 3 if rope else 0), epi
+    keep = (a, b, bias, out, cos, sin)
+
+    def fn():
+        _lib.check(_lib.lib().b200vit_gemm(C.byref(g), stream()), "gemm")
+    fn.keep = keep
+    return fn
+
+
+def main():
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+    res = {}
+    shapes = [
+        ("patch_embed", M, D, 1176, _lib.EPI_STORE_F32, None, False, torch.float32),
+        ("qkv_rope", M, 3 * D, D, _lib.EPI_QKV_ROPE, None, True, torch.bfloat16),
+        ("proj_resid", M, D, D, _lib.EPI_BIAS_RESIDUAL, None, False, torch.float32),
+        ("gateup_swiglu", M, 2 * IPAD, D, _lib.EPI_SWIGLU, IPAD, False, torch.bfloat16),
+        ("down_resid", M, D, IPAD, _lib.EPI_BIAS_RESIDUAL, None, False, torch.float32),
+        ("merger_fc1", M // 4, 4 * D, 4 * D, _lib.EPI_BIAS_GELU, None, False, torch.bfloat16),
+        ("merger_fc2", M // 4, 3584, 4 * D, _lib.EPI_BIAS_BF16, None, False, torch.bfloat16),
+    ]
+    for name, m, n, k, epi, ldo, rope, odt in shapes:
+        fn = gemm_fn(m, n, k, epi, ldo, rope, odt)
+        med, mn = timeit(fn, flush=flush)
+        tf = 2.0 * m * n * k / (med * 1e-3) / 1e12
+        res[name] = dict(ms=med, ms_min=mn, tflops=tf, m=m, n=n, k=k)
+        print(f"{name:16s} {m}x{n}x{k}  {med*1e3:8.1f} us  {tf:7.1f} TFLOP/s (min {mn*1e3:.1f} us)", flush=True)
+    # torch.matmul comparator (cuBLAS) for the same shapes
+    for name, m, n, k, *_ in shapes:
+        a = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+        b = torch.randn(n, k, device=DEV).to(torch.bfloat16)
+        med, mn = timeit(lambda: torch.matmul(a, b.t()), flush=flush)
+        print(f"cublas {name:16s} {med*1e3:8.1f} us  {2.0*m*n*k/(med*1e-3)/1e12:7.1f} TFLOP/s", flush=True)
+        res[name]["cublas_ms"] = med
+    # attention
+    for name, seg in (("attn_window", 64), ("attn_full", 1024)):
+        qkv = torch.randn(M, 3 * D, device=DEV).to(torch.bfloat16)
+        out = torch.zeros(M, D, dtype=torch.bfloat16, device=DEV)
+        t = vit.B200VisionTower(dict(depth=1, hidden_size=D, intermediate_size=I, num_heads=16, out_hidden_size=3584), device=DEV)
+        cu = np.arange(0, M + 1, seg, dtype=np.int32)
+        # timed through the test entry (includes a small H2D + sync): use many iterations as an upper bound
+        def fn():
+            _lib.check(_lib.lib().b200vit_attention(qkv.data_ptr(), out.data_ptr(), cu.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    len(cu) - 1, 16, stream()), "attn")
+        med, mn = timeit(fn, flush=flush)
+        fl = 4.0 * seg * D * M
+        res[name] = dict(ms=med, tflops=fl / (med * 1e-3) / 1e12)
+        print(f"{name:16s} {med*1e3:8.1f} us  {res[name]['tflops']:7.1f} TFLOP/s", flush=True)
+    # rmsnorm
+    x = torch.randn(M, D, device=DEV)
+    w = torch.ones(D, device=DEV)
+    o = torch.zeros(M, D, dtype=torch.bfloat16, device=DEV)
+    med, mn = timeit(lambda: _lib.check(_lib.lib().b200vit_rmsnorm(x.data_ptr(), w.data_ptr(), o.data_ptr(), M, D, 1e-6, stream()), "rms"), flush=flush)
+    res["rmsnorm"] = dict(ms=med, gbs=M * D * 6 / (med * 1e-3) / 1e9)
+    print(f"rmsnorm          {med*1e3:8.1f} us  {res['rmsnorm']['gbs']:7.1f} GB/s", flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/bench_ops.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
