@@ -151,6 +151,17 @@ int b200vit_forward(b200vit_plan* plan, const b200vit_weights* w, const void* d_
 /* Number of kernel launches one b200vit_forward enqueues for this plan.       */
 int b200vit_forward_launches(const b200vit_plan* plan, int with_frames);
 
+/* Per-kernel timing of the NEXT forward calls on this plan: a cudaEvent pair is recorded
+ * around every launch on the caller's stream.  profile_read waits for the last profiled
+ * forward and returns summed milliseconds and launch counts per kernel kind.           */
+enum {
+  B200VIT_K_OVERLAY_PATCHIFY = 0, B200VIT_K_PATCH_EMBED, B200VIT_K_RMSNORM, B200VIT_K_QKV, B200VIT_K_ATTN_WINDOW,
+  B200VIT_K_ATTN_FULL, B200VIT_K_PROJ, B200VIT_K_GATEUP, B200VIT_K_DOWN, B200VIT_K_MERGER_FC1, B200VIT_K_MERGER_FC2,
+  B200VIT_K_COUNT
+};
+int b200vit_profile_enable(b200vit_plan* plan, int enable);
+int b200vit_profile_read(b200vit_plan* plan, float* h_ms_by_kind, int32_t* h_count_by_kind);
+
 /* ------------------------------------------------------------------ single ops
  * The kernels behind b200vit_forward, exposed for parity tests and profiling. */
 

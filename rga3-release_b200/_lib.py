@@ -68,6 +68,8 @@ EXPORTS = {
     "b200vit_forward": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p, C.POINTER(Frames), C.POINTER(Overlay),
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200vit_forward_launches": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200vit_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200vit_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "b200vit_overlay_composite": (C.c_int, [C.POINTER(Frames), C.POINTER(Overlay), C.c_void_p, C.c_void_p]),
     "b200vit_overlay_patchify": (C.c_int, [C.POINTER(Frames), C.POINTER(Overlay), C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p]),
@@ -76,6 +78,9 @@ EXPORTS = {
     "b200vit_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p]),
     "b200vit_cast_to_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
 }
+
+KERNEL_KINDS = ["overlay_patchify", "patch_embed", "rmsnorm", "qkv_rope", "attn_window", "attn_full", "proj_resid",
+                "gateup_swiglu", "down_resid", "merger_fc1", "merger_fc2"]
 
 _lib = None
 

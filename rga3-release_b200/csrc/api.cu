@@ -33,6 +33,11 @@ struct b200vit_plan {
   float* d_sin = nullptr;
   AttnWork* d_work_window = nullptr;
   AttnWork* d_work_full = nullptr;
+  // optional per-launch profiling (cudaEvent pairs around every launch of a forward)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;       // 2 per launch
+  std::vector<int> ev_kind;          // B200VIT_K_* per launch
+  size_t ev_used = 0;
 };
 
 namespace {
@@ -137,6 +142,31 @@ int ensure_uploaded(b200vit_plan* p) {
   return 0;
 }
 
+// Records an event pair around one launch when profiling is on.
+struct Prof {
+  b200vit_plan* p;
+  cudaStream_t st;
+  void begin(int kind) {
+    if (!p->profile) return;
+    if (p->ev_used + 2 > p->ev.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        p->ev.push_back(e);
+      }
+      p->ev_kind.push_back(kind);
+    } else {
+      p->ev_kind[p->ev_used / 2] = kind;
+    }
+    cudaEventRecord(p->ev[p->ev_used], st);
+  }
+  void end() {
+    if (!p->profile) return;
+    cudaEventRecord(p->ev[p->ev_used + 1], st);
+    p->ev_used += 2;
+  }
+};
+
 bool is_fullatt(const b200vit_cfg& c, int layer) {
   for (int i = 0; i < c.n_fullatt; ++i)
     if (c.fullatt[i] == layer) return true;
@@ -215,6 +245,7 @@ void b200vit_plan_destroy(b200vit_plan* p) {
   cudaFree(p->d_sin);
   cudaFree(p->d_work_window);
   cudaFree(p->d_work_full);
+  for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
   delete p;
 }
 
@@ -269,6 +300,8 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
   void* act = ws + p->off_act;
   void* pv = ws + p->off_pv;
 
+  Prof prof{p, stream};
+  p->ev_used = 0;
   const void* a0 = d_pixel_values;
   if (frames) {
     if (p->grid.size() != 3) return fail(B200VIT_EINVAL, "forward: the frames entry takes a single-clip plan");
@@ -276,7 +309,9 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     if (frames->h != p->grid[1] * c.patch || frames->w != p->grid[2] * c.patch ||
         (frames->t != t_need && frames->t != t_need - (c.temporal_patch - 1)))
       return fail(B200VIT_EINVAL, "forward: frames shape does not match the plan's grid_thw");
+    prof.begin(B200VIT_K_OVERLAY_PATCHIFY);
     if ((rc = launch_overlay_patchify(*frames, overlay, c.patch, c.temporal_patch, c.merge, pv, nullptr, stream))) return rc;
+    prof.end();
     a0 = pv;
   }
   b200vit_gemm_args g;
@@ -284,47 +319,90 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
   // patch embed (+ window reorder in the store)
   g.d_a = a0, g.d_b = w->patch_w, g.d_out = x, g.d_row_map = p->d_row_map;
   g.m = M, g.n = D, g.k = p->kpe, g.ldo = D, g.epilogue = B200VIT_EPI_STORE_F32;
+  prof.begin(B200VIT_K_PATCH_EMBED);
   if ((rc = launch_gemm(g, stream))) return rc;
+  prof.end();
 
   for (int l = 0; l < c.depth; ++l) {
     const b200vit_layer_weights& lw = w->layers[l];
     const bool full = is_fullatt(c, l);
+    prof.begin(B200VIT_K_RMSNORM);
     if ((rc = launch_rmsnorm(x, lw.norm1_w, h, M, D, 1e-6f, stream))) return rc;
+    prof.end();
     std::memset(&g, 0, sizeof(g));
     g.d_a = h, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_cos = p->d_cos, g.d_sin = p->d_sin;
     g.m = M, g.n = 3 * D, g.k = D, g.ldo = 3 * D, g.rope_cols = 2 * D, g.epilogue = B200VIT_EPI_QKV_ROPE;
+    prof.begin(B200VIT_K_QKV);
     if ((rc = launch_gemm(g, stream))) return rc;
+    prof.end();
+    prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
     if ((rc = launch_attention(qkv, attn, full ? p->d_work_full : p->d_work_window,
                                static_cast<int>(full ? p->work_full.size() : p->work_window.size()), c.heads, stream)))
       return rc;
+    prof.end();
     std::memset(&g, 0, sizeof(g));
     g.d_a = attn, g.d_b = lw.proj_w, g.d_out = x, g.d_bias = lw.proj_b;
     g.m = M, g.n = D, g.k = D, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
+    prof.begin(B200VIT_K_PROJ);
     if ((rc = launch_gemm(g, stream))) return rc;
+    prof.end();
+    prof.begin(B200VIT_K_RMSNORM);
     if ((rc = launch_rmsnorm(x, lw.norm2_w, h, M, D, 1e-6f, stream))) return rc;
+    prof.end();
     std::memset(&g, 0, sizeof(g));
     g.d_a = h, g.d_b = lw.gateup_w, g.d_out = act, g.d_bias = lw.gateup_b;
     g.m = M, g.n = 2 * p->ipad, g.k = D, g.ldo = p->ipad, g.epilogue = B200VIT_EPI_SWIGLU;
+    prof.begin(B200VIT_K_GATEUP);
     if ((rc = launch_gemm(g, stream))) return rc;
+    prof.end();
     std::memset(&g, 0, sizeof(g));
     g.d_a = act, g.d_b = lw.down_w, g.d_out = x, g.d_bias = lw.down_b;
     g.m = M, g.n = D, g.k = p->ipad, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
+    prof.begin(B200VIT_K_DOWN);
     if ((rc = launch_gemm(g, stream))) return rc;
+    prof.end();
   }
   if (d_last_hidden)
     B200_CUDA_OK(cudaMemcpyAsync(d_last_hidden, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
   // merger (HF :133-146) + un-reorder (:512-513)
   const int Mm = M / p->unit, Dm = D * p->unit;
+  prof.begin(B200VIT_K_RMSNORM);
   if ((rc = launch_rmsnorm(x, w->merger_ln_w, h, M, D, 1e-6f, stream))) return rc;
+  prof.end();
   std::memset(&g, 0, sizeof(g));
   g.d_a = h, g.d_b = w->merger_fc1_w, g.d_out = attn, g.d_bias = w->merger_fc1_b;
   g.m = Mm, g.n = Dm, g.k = Dm, g.ldo = Dm, g.epilogue = B200VIT_EPI_BIAS_GELU;
+  prof.begin(B200VIT_K_MERGER_FC1);
   if ((rc = launch_gemm(g, stream))) return rc;
+  prof.end();
   std::memset(&g, 0, sizeof(g));
   g.d_a = attn, g.d_b = w->merger_fc2_w, g.d_out = d_out, g.d_bias = w->merger_fc2_b, g.d_row_map = p->d_merge_map;
   g.m = Mm, g.n = c.out_hidden, g.k = Dm, g.ldo = c.out_hidden;
   g.epilogue = out_f32 ? B200VIT_EPI_BIAS_F32 : B200VIT_EPI_BIAS_BF16;
+  prof.begin(B200VIT_K_MERGER_FC2);
   if ((rc = launch_gemm(g, stream))) return rc;
+  prof.end();
+  return 0;
+}
+
+int b200vit_profile_enable(b200vit_plan* p, int enable) {
+  if (!p) return fail(B200VIT_EINVAL, "profile_enable: null plan");
+  p->profile = enable != 0;
+  p->ev_used = 0;
+  return 0;
+}
+
+int b200vit_profile_read(b200vit_plan* p, float* h_ms_by_kind, int32_t* h_count_by_kind) {
+  if (!p || !h_ms_by_kind || !h_count_by_kind) return fail(B200VIT_EINVAL, "profile_read: null argument");
+  for (int i = 0; i < B200VIT_K_COUNT; ++i) h_ms_by_kind[i] = 0.f, h_count_by_kind[i] = 0;
+  for (size_t i = 0; i + 1 < p->ev_used; i += 2) {
+    B200_CUDA_OK(cudaEventSynchronize(p->ev[i + 1]));
+    float ms = 0.f;
+    B200_CUDA_OK(cudaEventElapsedTime(&ms, p->ev[i], p->ev[i + 1]));
+    const int k = p->ev_kind[i / 2];
+    h_ms_by_kind[k] += ms;
+    h_count_by_kind[k] += 1;
+  }
   return 0;
 }
 

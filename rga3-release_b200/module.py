@@ -293,7 +293,8 @@ class B200VisionTower(nn.Module):
         return static_out
 
     @torch.no_grad()
-    def forward_frames(self, frames_u8: torch.Tensor, overlay: Optional[OverlaySpec] = None, grid_thw=None):
+    def forward_frames(self, frames_u8: torch.Tensor, overlay: Optional[OverlaySpec] = None, grid_thw=None,
+                       out: Optional[torch.Tensor] = None):
         """Fused entry: uint8 frames [T,H,W,3] (CUDA) + optional STOM overlay -> merged embeddings.
         Equivalent to PIL overlay -> Qwen2VLVideoProcessor(do_resize=False) -> tower."""
         if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
@@ -307,9 +308,24 @@ class B200VisionTower(nn.Module):
         fc = _lib.Frames(fr.data_ptr(), t, h, w)
         oc = overlay.to_c(t) if overlay is not None else None
         out_dtype = torch.float32 if self.output_fp32 else self._dtype
-        out = torch.empty(plan.m // self.spatial_merge_unit, self.out_hidden_size, dtype=out_dtype, device=fr.device)
+        shape = (plan.m // self.spatial_merge_unit, self.out_hidden_size)
+        if out is None:
+            out = torch.empty(shape, dtype=out_dtype, device=fr.device)
+        elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError(f"out must be a contiguous bf16/fp32 tensor of shape {shape}")
         self._run(plan, None, fc, oc, out, None)
         return self._wrap(out, None)
+
+    def profile(self, grid_thw, enable: bool):
+        """Per-kernel cudaEvent timing of the following forwards on this grid's plan."""
+        _lib.check(_lib.lib().b200vit_profile_enable(self.plan_for(grid_thw).handle, 1 if enable else 0), "profile_enable")
+
+    def profile_read(self, grid_thw):
+        """{kind: (total_ms, launches)} for the last profiled forward."""
+        n = len(_lib.KERNEL_KINDS)
+        ms, cnt = (C.c_float * n)(), (C.c_int32 * n)()
+        _lib.check(_lib.lib().b200vit_profile_read(self.plan_for(grid_thw).handle, ms, cnt), "profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.KERNEL_KINDS)}
 
     def launches_per_forward(self, grid_thw, with_frames=False) -> int:
         return int(_lib.lib().b200vit_forward_launches(self.plan_for(grid_thw).handle, 1 if with_frames else 0))
