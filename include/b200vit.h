@@ -74,7 +74,8 @@ enum {
   B200VIT_PLAN_ROW_MAP = 5,        /* int32 [M]   patch row -> row in window order       */
   B200VIT_PLAN_ROPE_COS = 6,       /* fp32  [M,head_dim/2] window order                  */
   B200VIT_PLAN_ROPE_SIN = 7,       /* fp32  [M,head_dim/2] window order                  */
-  B200VIT_PLAN_POS_IDS = 8         /* int32 [M,2] (hpos,wpos), ORIGINAL patch order       */
+  B200VIT_PLAN_POS_IDS = 8,        /* int32 [M,2] (hpos,wpos), ORIGINAL patch order       */
+  B200VIT_PLAN_ROPE_PACKED = 9     /* fp16x2 [M,head_dim/2] (cos,sin) pairs as the QKV epilogue reads them */
 };
 /* Copies a host-side plan array into h_dst (cap bytes).  Returns the number of
  * bytes the array holds (so a call with cap = 0 sizes it), negative on error.  */
@@ -187,8 +188,7 @@ typedef struct b200vit_gemm_args {
   void* d_out;          /* see epilogue                                               */
   const float* d_bias;  /* [N] or NULL                                                */
   const int32_t* d_row_map; /* [M] or NULL (identity)                                  */
-  const float* d_cos;   /* QKV_ROPE: [M, 40]                                          */
-  const float* d_sin;
+  const void* d_rope;   /* QKV_ROPE: [M, 40] fp16 pairs (cos, sin), 4 bytes per entry, window order */
   int32_t m, n, k;
   int32_t ldo;          /* leading dimension of out, in elements                       */
   int32_t rope_cols;    /* QKV_ROPE: columns [0, rope_cols) are rotated (= 2D)         */

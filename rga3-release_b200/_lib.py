@@ -17,7 +17,7 @@ EPI_STORE_F32, EPI_QKV_ROPE, EPI_BIAS_RESIDUAL, EPI_SWIGLU, EPI_BIAS_GELU, EPI_B
 LAYER_NONE, LAYER_RGBA, LAYER_PALETTE, LAYER_BOX = range(4)
 FRAME_NONE, FRAME_LAYER, FRAME_CIRCLE = range(3)
 (PLAN_M, PLAN_WINDOW_INDEX, PLAN_REVERSE_INDEX, PLAN_CU_WINDOW, PLAN_CU_FULL, PLAN_ROW_MAP, PLAN_ROPE_COS,
- PLAN_ROPE_SIN, PLAN_POS_IDS) = range(9)
+ PLAN_ROPE_SIN, PLAN_POS_IDS, PLAN_ROPE_PACKED) = range(10)
 
 
 class Cfg(C.Structure):
@@ -53,7 +53,7 @@ class Frames(C.Structure):
 
 class GemmArgs(C.Structure):
     _fields_ = [("d_a", C.c_void_p), ("d_b", C.c_void_p), ("d_out", C.c_void_p), ("d_bias", C.c_void_p),
-                ("d_row_map", C.c_void_p), ("d_cos", C.c_void_p), ("d_sin", C.c_void_p), ("m", C.c_int32),
+                ("d_row_map", C.c_void_p), ("d_rope", C.c_void_p), ("m", C.c_int32),
                 ("n", C.c_int32), ("k", C.c_int32), ("ldo", C.c_int32), ("rope_cols", C.c_int32),
                 ("epilogue", C.c_int32)]
 

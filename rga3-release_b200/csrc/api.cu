@@ -1,5 +1,7 @@
 // C ABI: plan (everything derived from grid_thw), the whole-path forward and the
 // single-op entry points.  See include/b200vit.h for the contract.
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -20,6 +22,7 @@ struct b200vit_plan {
   std::vector<int64_t> window_index, reverse_index;
   std::vector<int32_t> cu_window, cu_full, row_map, merge_map, pos_ids;
   std::vector<float> rope_cos, rope_sin;  // [M, head_dim/2] in window order
+  std::vector<uint32_t> rope_packed;      // same table as fp16 (cos, sin) pairs -- what the QKV epilogue reads
   std::vector<AttnWork> work_window, work_full;
   // workspace layout (byte offsets)
   size_t off_x = 0, off_h = 0, off_qkv = 0, off_attn = 0, off_act = 0, off_pv = 0, ws_bytes = 0;
@@ -29,8 +32,7 @@ struct b200vit_plan {
   bool uploaded = false;
   int32_t* d_row_map = nullptr;
   int32_t* d_merge_map = nullptr;
-  float* d_cos = nullptr;
-  float* d_sin = nullptr;
+  uint32_t* d_rope = nullptr;
   AttnWork* d_work_window = nullptr;
   AttnWork* d_work_full = nullptr;
   // optional per-launch profiling (cudaEvent pairs around every launch of a forward)
@@ -118,6 +120,11 @@ void build_rope(b200vit_plan& p) {
               }
             }
   }
+  p.rope_packed.resize(p.rope_cos.size());
+  for (size_t i = 0; i < p.rope_cos.size(); ++i) {
+    const __half2 h = __floats2half2_rn(p.rope_cos[i], p.rope_sin[i]);
+    std::memcpy(&p.rope_packed[i], &h, 4);
+  }
 }
 
 template <typename T>
@@ -134,8 +141,7 @@ int ensure_uploaded(b200vit_plan* p) {
   int rc;
   if ((rc = upload(&p->d_row_map, p->row_map))) return rc;
   if ((rc = upload(&p->d_merge_map, p->merge_map))) return rc;
-  if ((rc = upload(&p->d_cos, p->rope_cos))) return rc;
-  if ((rc = upload(&p->d_sin, p->rope_sin))) return rc;
+  if ((rc = upload(&p->d_rope, p->rope_packed))) return rc;
   if ((rc = upload(&p->d_work_window, p->work_window))) return rc;
   if ((rc = upload(&p->d_work_full, p->work_full))) return rc;
   p->uploaded = true;
@@ -241,8 +247,7 @@ void b200vit_plan_destroy(b200vit_plan* p) {
   if (!p) return;
   cudaFree(p->d_row_map);
   cudaFree(p->d_merge_map);
-  cudaFree(p->d_cos);
-  cudaFree(p->d_sin);
+  cudaFree(p->d_rope);
   cudaFree(p->d_work_window);
   cudaFree(p->d_work_full);
   for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
@@ -263,6 +268,7 @@ int64_t b200vit_plan_get(const b200vit_plan* p, int which, void* h_dst, size_t c
     case B200VIT_PLAN_ROPE_COS: src = p->rope_cos.data(), bytes = p->rope_cos.size() * 4; break;
     case B200VIT_PLAN_ROPE_SIN: src = p->rope_sin.data(), bytes = p->rope_sin.size() * 4; break;
     case B200VIT_PLAN_POS_IDS: src = p->pos_ids.data(), bytes = p->pos_ids.size() * 4; break;
+    case B200VIT_PLAN_ROPE_PACKED: src = p->rope_packed.data(), bytes = p->rope_packed.size() * 4; break;
     default: return fail(B200VIT_EINVAL, "plan_get: unknown array id");
   }
   if (h_dst && cap >= bytes) std::memcpy(h_dst, src, bytes);
@@ -330,7 +336,7 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     if ((rc = launch_rmsnorm(x, lw.norm1_w, h, M, D, 1e-6f, stream))) return rc;
     prof.end();
     std::memset(&g, 0, sizeof(g));
-    g.d_a = h, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_cos = p->d_cos, g.d_sin = p->d_sin;
+    g.d_a = h, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_rope = p->d_rope;
     g.m = M, g.n = 3 * D, g.k = D, g.ldo = 3 * D, g.rope_cols = 2 * D, g.epilogue = B200VIT_EPI_QKV_ROPE;
     prof.begin(B200VIT_K_QKV);
     if ((rc = launch_gemm(g, stream))) return rc;

@@ -8,13 +8,20 @@
 // follows each of them (2-D RoPE :149-167, residual adds :313/:320, SiLU-gate :88,
 // exact GELU :139, window reorder :478-481, un-reorder :512-513).
 //
-// Structure: persistent CTAs (one per SM), warp-specialised:
-//   warp 0      TMA producer   (A and B tiles, 128-B swizzle, STAGES-deep mbarrier ring)
-//   warp 1      MMA issuer     (one thread, tcgen05.mma 128 x BN x 16, two TMEM accumulators)
+// Structure: persistent CTA pairs (one cluster of 2 per TPC), warp-specialised:
+//   warp 0      TMA producer   (own 128 rows of A + half of the B tile, 128-B swizzle, mbarrier ring)
+//   warp 1      MMA issuer     (leader CTA, one thread: tcgen05.mma.cta_group::2, 256 x BN x 16,
+//                               two TMEM accumulator stages)
 //   warp 2      TMEM allocator
-//   warps 4..   epilogue       (EG groups of 4 warps; tcgen05.ld -> registers -> global)
-// so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 4..   epilogue       (EG groups of 4 warps: tcgen05.ld -> registers -> swizzled smem ->
+//                               TMA store / TMA reduce-add), overlapping the next tile's main loop.
+// Global traffic of the hot epilogues goes through the TMA engine: a thread owns one accumulator
+// ROW, so direct stores would be 32 separate sectors per instruction (measured: the first version
+// of this kernel was epilogue-bound on LSU wavefronts, profiles/r01_*).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -24,72 +31,98 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct GemmParams {
   void* out;
   const float* bias;
   const int32_t* row_map;
-  const float* cos;
-  const float* sin;
+  const uint32_t* rope;  // [M, 40] half2 (cos, sin)
   int m, n, k, ldo, rope_cols;
 };
 
-template <int BN>
+// staging bytes per epilogue warp (TMA-store epilogues), 0 = direct global stores
+__host__ __device__ constexpr int epi_stage_bytes(int epi) {
+  return epi == B200VIT_EPI_QKV_ROPE        ? 32 * 160
+         : epi == B200VIT_EPI_BIAS_RESIDUAL ? 2 * 4096
+         : epi == B200VIT_EPI_SWIGLU        ? 4096
+         : epi == B200VIT_EPI_BIAS_GELU     ? 2 * 4096
+                                            : 0;
+}
+
+// PAIR = true: two CTAs of a cluster cooperate on a 256 x BN tile with tcgen05.mma.cta_group::2 --
+// each CTA stages its own 128 rows of A and HALF of the B tile (1.5x less L2->SM operand traffic).
+template <int BN, int EG, int EPI, bool PAIR>
 struct TileCfg {
-  static constexpr int STAGES = (BN > 128) ? 4 : 6;
+  static constexpr int BN_LOAD = PAIR ? BN / 2 : BN;  // B rows staged by one CTA
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN_LOAD * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARPS = 4 * EG;
+  static constexpr int STG_WARP = (epi_stage_bytes(EPI) + 1023) / 1024 * 1024;
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - STG_BYTES;
+  static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;  // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  static_assert(STAGES >= 3, "not enough shared memory for the pipeline");
+  static_assert((2 * STAGES + 4) * 8 + 16 <= BAR_BYTES, "barrier area too small");
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 bias4(const float* bias, int col, int n) {
+  return (col + 4 <= n) ? ldg4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// 16-byte chunk j of row `lane` inside a [32 rows x 128 B] SWIZZLE_128B box at `base` (1024-aligned)
+__device__ __forceinline__ uint32_t swz128(uint32_t base, int lane, int j) {
+  return base + lane * 128 + ((j ^ (lane & 7)) << 4);
+}
 
 // ------------------------------------------------------------------ epilogues
 // Each epilogue thread owns one accumulator row (TMEM lane) and CW consecutive columns.
+// `stg` = this warp's staging buffer (shared address), `row0` = first row of the warp's 32-row slab.
 template <int EPI, int CW>
-__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col0, const GemmParams& p) {
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane, int col0, const GemmParams& p,
+                                              const CUtensorMap* tma_out, uint32_t stg) {
+  const int row = row0 + lane;
   const bool row_ok = row < p.m;
   if constexpr (EPI == B200VIT_EPI_QKV_ROPE) {
     static_assert(CW == 80, "QKV epilogue handles one 80-wide head per warp group");
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+    if (lane == 0) bulk_wait_read<0>();  // previous tile's store has drained the staging buffer
+    __syncwarp();
+    const uint32_t srow = stg + lane * 160;
     if (col0 < p.rope_cols) {
-      const float* cs = p.cos + static_cast<size_t>(row) * 40;
-      const float* sn = p.sin + static_cast<size_t>(row) * 40;
+      const uint4* cs = reinterpret_cast<const uint4*>(p.rope + static_cast<size_t>(row_ok ? row : 0) * 40);
 #pragma unroll
       for (int d0 = 0; d0 < 40; d0 += 8) {
         uint32_t lo[8], hi[8];
         tmem_ld8(taddr + d0, lo);
         tmem_ld8(taddr + 40 + d0, hi);
+        const uint4 t0 = __ldg(cs + (d0 >> 2)), t1 = __ldg(cs + (d0 >> 2) + 1);
+        const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        float bl[8], bh[8];
+        *reinterpret_cast<float4*>(&bl[0]) = ldg4(p.bias + col0 + d0);
+        *reinterpret_cast<float4*>(&bl[4]) = ldg4(p.bias + col0 + d0 + 4);
+        *reinterpret_cast<float4*>(&bh[0]) = ldg4(p.bias + col0 + 40 + d0);
+        *reinterpret_cast<float4*>(&bh[4]) = ldg4(p.bias + col0 + 40 + d0 + 4);
         tmem_ld_wait();
-        if (row_ok) {
-          float c[8], s[8], bl[8], bh[8];
-          *reinterpret_cast<float4*>(&c[0]) = ldg4(cs + d0);
-          *reinterpret_cast<float4*>(&c[4]) = ldg4(cs + d0 + 4);
-          *reinterpret_cast<float4*>(&s[0]) = ldg4(sn + d0);
-          *reinterpret_cast<float4*>(&s[4]) = ldg4(sn + d0 + 4);
-          *reinterpret_cast<float4*>(&bl[0]) = ldg4(p.bias + col0 + d0);
-          *reinterpret_cast<float4*>(&bl[4]) = ldg4(p.bias + col0 + d0 + 4);
-          *reinterpret_cast<float4*>(&bh[0]) = ldg4(p.bias + col0 + 40 + d0);
-          *reinterpret_cast<float4*>(&bh[4]) = ldg4(p.bias + col0 + 40 + d0 + 4);
-          uint32_t olo[4], ohi[4];
+        uint32_t olo[4], ohi[4];
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float x0 = __uint_as_float(lo[j]) + bl[j], x1 = __uint_as_float(lo[j + 1]) + bl[j + 1];
-            float y0 = __uint_as_float(hi[j]) + bh[j], y1 = __uint_as_float(hi[j + 1]) + bh[j + 1];
-            // rotate_half: out[d] = x*cos - y*sin ; out[d+40] = y*cos + x*sin   (HF :149-167)
-            olo[j >> 1] = pack_bf16x2(x0 * c[j] - y0 * s[j], x1 * c[j + 1] - y1 * s[j + 1]);
-            ohi[j >> 1] = pack_bf16x2(y0 * c[j] + x0 * s[j], y1 * c[j + 1] + x1 * s[j + 1]);
-          }
-          *reinterpret_cast<uint4*>(out + d0) = make_uint4(olo[0], olo[1], olo[2], olo[3]);
-          *reinterpret_cast<uint4*>(out + 40 + d0) = make_uint4(ohi[0], ohi[1], ohi[2], ohi[3]);
+        for (int j = 0; j < 8; j += 2) {
+          const float2 cs0 = __half22float2(*reinterpret_cast<const __half2*>(&tw[j]));      // (cos, sin)
+          const float2 cs1 = __half22float2(*reinterpret_cast<const __half2*>(&tw[j + 1]));
+          const float x0 = __uint_as_float(lo[j]) + bl[j], x1 = __uint_as_float(lo[j + 1]) + bl[j + 1];
+          const float y0 = __uint_as_float(hi[j]) + bh[j], y1 = __uint_as_float(hi[j + 1]) + bh[j + 1];
+          // rotate_half: out[d] = x*cos - y*sin ; out[d+40] = y*cos + x*sin   (HF :149-167)
+          olo[j >> 1] = pack_bf16x2(x0 * cs0.x - y0 * cs0.y, x1 * cs1.x - y1 * cs1.y);
+          ohi[j >> 1] = pack_bf16x2(y0 * cs0.x + x0 * cs0.y, y1 * cs1.x + x1 * cs1.y);
         }
+        st_shared_v4(srow + d0 * 2, olo[0], olo[1], olo[2], olo[3]);
+        st_shared_v4(srow + 80 + d0 * 2, ohi[0], ohi[1], ohi[2], ohi[3]);
       }
     } else {
 #pragma unroll
@@ -97,20 +130,112 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col0,
         uint32_t v[16];
         tmem_ld16(taddr + d0, v);
         tmem_ld_wait();
-        if (row_ok) {
-          uint32_t o[8];
+        uint32_t o[8];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 b = ldg4(p.bias + col0 + d0 + j);
-            o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y);
-            o[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
-          }
-          *reinterpret_cast<uint4*>(out + d0) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(out + d0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b = ldg4(p.bias + col0 + d0 + j);
+          o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y);
+          o[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
         }
+        st_shared_v4(srow + d0 * 2, o[0], o[1], o[2], o[3]);
+        st_shared_v4(srow + d0 * 2 + 16, o[4], o[5], o[6], o[7]);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tma_out, stg, col0, row0);
+      bulk_commit();
+    }
+  } else if constexpr (EPI == B200VIT_EPI_BIAS_RESIDUAL) {
+    // x += acc + bias through TMA reduce-add (fp32 add performed at L2): no residual loads on the SM.
+    static_assert(CW % 32 == 0, "32-column chunks");
+#pragma unroll
+    for (int c = 0; c < CW; c += 32) {
+      const uint32_t buf = stg + ((c >> 5) & 1) * 4096;
+      uint32_t v[32];
+      tmem_ld32(taddr + c, v);
+      if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer (two chunks ago) has read it
+      __syncwarp();
+      const int col = col0 + c;
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = bias4(p.bias, col + 4 * j, p.n);
+        st_shared_v4(swz128(buf, lane, j), __float_as_uint(__uint_as_float(v[4 * j]) + b.x),
+                     __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y),
+                     __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z),
+                     __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(tma_out, buf, col, row0);
+        bulk_commit();
+      }
+    }
+  } else if constexpr (EPI == B200VIT_EPI_SWIGLU) {
+    // columns are (gate, up) pairs; CW = 128 accumulator columns -> 64 bf16 outputs = one 128-byte box row
+    static_assert(CW == 128, "SwiGLU epilogue expects 128 accumulator columns per warp");
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CW; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c, v);
+      const int col = col0 + c;
+      float4 b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = bias4(p.bias, col + 4 * j, p.n);
+      tmem_ld_wait();
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g0 = __uint_as_float(v[4 * j]) + b[j].x, u0 = __uint_as_float(v[4 * j + 1]) + b[j].y;
+        const float g1 = __uint_as_float(v[4 * j + 2]) + b[j].z, u1 = __uint_as_float(v[4 * j + 3]) + b[j].w;
+        o[j] = pack_bf16x2(silu_f(g0) * u0, silu_f(g1) * u1);
+      }
+      st_shared_v4(swz128(stg, lane, (c >> 4)), o[0], o[1], o[2], o[3]);
+      st_shared_v4(swz128(stg, lane, (c >> 4) + 1), o[4], o[5], o[6], o[7]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tma_out, stg, col0 >> 1, row0);
+      bulk_commit();
+    }
+  } else if constexpr (EPI == B200VIT_EPI_BIAS_GELU) {
+    static_assert(CW % 64 == 0, "64-column boxes");
+#pragma unroll
+    for (int c = 0; c < CW; c += 64) {
+      const uint32_t buf = stg + ((c >> 6) & 1) * 4096;
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c + 32 * h, v);
+        const int col = col0 + c + 32 * h;
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = bias4(p.bias, col + 8 * j, p.n), b1 = bias4(p.bias, col + 8 * j + 4, p.n);
+          st_shared_v4(swz128(buf, lane, 4 * h + j),
+                       pack_bf16x2(gelu_erf_f(__uint_as_float(v[8 * j]) + b0.x), gelu_erf_f(__uint_as_float(v[8 * j + 1]) + b0.y)),
+                       pack_bf16x2(gelu_erf_f(__uint_as_float(v[8 * j + 2]) + b0.z), gelu_erf_f(__uint_as_float(v[8 * j + 3]) + b0.w)),
+                       pack_bf16x2(gelu_erf_f(__uint_as_float(v[8 * j + 4]) + b1.x), gelu_erf_f(__uint_as_float(v[8 * j + 5]) + b1.y)),
+                       pack_bf16x2(gelu_erf_f(__uint_as_float(v[8 * j + 6]) + b1.z), gelu_erf_f(__uint_as_float(v[8 * j + 7]) + b1.w)));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tma_out, buf, col0 + c, row0);
+        bulk_commit();
       }
     }
   } else {
+    // row-mapped outputs (window reorder of the patch embed, un-reorder of the merger): direct stores
     static_assert(CW % 32 == 0, "generic epilogues work in 32-column chunks");
     const int orow = (row_ok && p.row_map != nullptr) ? p.row_map[row] : row;
 #pragma unroll 1
@@ -118,80 +243,33 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col0,
       uint32_t v[32];
       tmem_ld32(taddr + c, v);
       const int col = col0 + c;
-      if constexpr (EPI == B200VIT_EPI_BIAS_RESIDUAL) {
-        // issue the residual loads before waiting on TMEM so the two latencies overlap
-        float4 r[8];
-        float* xp = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      if constexpr (EPI == B200VIT_EPI_STORE_F32 || EPI == B200VIT_EPI_BIAS_F32) {
+        float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo + col;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          r[j] = (row_ok && col + 4 * j + 4 <= p.n) ? *reinterpret_cast<const float4*>(xp + 4 * j)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (col + 4 * j + 4 <= p.n) {
-              float4 b = ldg4(p.bias + col + 4 * j);
-              r[j].x += __uint_as_float(v[4 * j]) + b.x;
-              r[j].y += __uint_as_float(v[4 * j + 1]) + b.y;
-              r[j].z += __uint_as_float(v[4 * j + 2]) + b.z;
-              r[j].w += __uint_as_float(v[4 * j + 3]) + b.w;
-              *reinterpret_cast<float4*>(xp + 4 * j) = r[j];
+        for (int j = 0; j < 8; ++j) {
+          if (col + 4 * j + 4 <= p.n) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            if constexpr (EPI == B200VIT_EPI_BIAS_F32) {
+              const float4 b = ldg4(p.bias + col + 4 * j);
+              o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
             }
+            *reinterpret_cast<float4*>(op + 4 * j) = o;
           }
         }
-      } else {
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        if constexpr (EPI == B200VIT_EPI_STORE_F32 || EPI == B200VIT_EPI_BIAS_F32) {
-          float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo + col;
+      } else {  // BIAS_BF16
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (col + 4 * j + 4 <= p.n) {
-              float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-              if constexpr (EPI == B200VIT_EPI_BIAS_F32) {
-                float4 b = ldg4(p.bias + col + 4 * j);
-                o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
-              }
-              *reinterpret_cast<float4*>(op + 4 * j) = o;
-            }
-          }
-        } else if constexpr (EPI == B200VIT_EPI_SWIGLU) {
-          // columns are (gate, up) pairs; 32 accumulator columns -> 16 outputs
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + (col >> 1);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (col + 16 * h + 16 <= p.n) {
-              uint32_t o[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 b = ldg4(p.bias + col + 16 * h + 4 * j);
-                const int i = 16 * h + 4 * j;
-                float g0 = __uint_as_float(v[i]) + b.x, u0 = __uint_as_float(v[i + 1]) + b.y;
-                float g1 = __uint_as_float(v[i + 2]) + b.z, u1 = __uint_as_float(v[i + 3]) + b.w;
-                o[j] = pack_bf16x2(silu_f(g0) * u0, silu_f(g1) * u1);
-              }
-              *reinterpret_cast<uint4*>(op + 8 * h) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-          }
-        } else {  // BIAS_GELU, BIAS_BF16
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col;
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            if (col + 8 * h + 8 <= p.n) {
-              float4 b0 = ldg4(p.bias + col + 8 * h), b1 = ldg4(p.bias + col + 8 * h + 4);
-              float f[8] = {__uint_as_float(v[8 * h]) + b0.x,     __uint_as_float(v[8 * h + 1]) + b0.y,
-                            __uint_as_float(v[8 * h + 2]) + b0.z, __uint_as_float(v[8 * h + 3]) + b0.w,
-                            __uint_as_float(v[8 * h + 4]) + b1.x, __uint_as_float(v[8 * h + 5]) + b1.y,
-                            __uint_as_float(v[8 * h + 6]) + b1.z, __uint_as_float(v[8 * h + 7]) + b1.w};
-              if constexpr (EPI == B200VIT_EPI_BIAS_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = gelu_erf_f(f[j]);
-              }
-              *reinterpret_cast<uint4*>(op + 8 * h) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                                 pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            }
+        for (int h = 0; h < 4; ++h) {
+          if (col + 8 * h + 8 <= p.n) {
+            const float4 b0 = ldg4(p.bias + col + 8 * h), b1 = ldg4(p.bias + col + 8 * h + 4);
+            *reinterpret_cast<uint4*>(op + 8 * h) =
+                make_uint4(pack_bf16x2(__uint_as_float(v[8 * h]) + b0.x, __uint_as_float(v[8 * h + 1]) + b0.y),
+                           pack_bf16x2(__uint_as_float(v[8 * h + 2]) + b0.z, __uint_as_float(v[8 * h + 3]) + b0.w),
+                           pack_bf16x2(__uint_as_float(v[8 * h + 4]) + b1.x, __uint_as_float(v[8 * h + 5]) + b1.y),
+                           pack_bf16x2(__uint_as_float(v[8 * h + 6]) + b1.z, __uint_as_float(v[8 * h + 7]) + b1.w));
           }
         }
       }
@@ -200,20 +278,24 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col0,
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BN, int EG, int EPI>
+template <int BN, int EG, int EPI, bool PAIR>
 __global__ void __launch_bounds__(128 + 128 * EG, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const GemmParams p) {
-  using C = TileCfg<BN>;
+                    const __grid_constant__ CUtensorMap tma_out, const GemmParams p) {
+  using C = TileCfg<BN, EG, EPI, PAIR>;
   constexpr int STAGES = C::STAGES;
   constexpr int CW = BN / EG;
+  constexpr int NCTA = PAIR ? 2 : 1;
+  constexpr int MT = BM * NCTA;  // rows of C per scheduled tile
   static_assert(BN % EG == 0 && BN % 16 == 0 && BN <= 256, "invalid tile");
+  static_assert(C::B_BYTES % 1024 == 0, "B tile must keep 1024-byte stage alignment");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * C::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint8_t* sStg = smem + STAGES * C::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStg + C::STG_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -221,48 +303,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  const int unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_units = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int num_n = (p.n + BN - 1) / BN;
-  const int num_m = (p.m + BM - 1) / BM;
+  const int num_m = (p.m + MT - 1) / MT;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.k + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (epi_stage_bytes(EPI) > 0) tma_prefetch_desc(&tma_out);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], NCTA);  // one arrival per producing CTA (+ the TMA transaction bytes)
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4 * EG);  // one arrival per epilogue warp
+      mbar_init(&tempty[i], 4 * EG * NCTA);  // one arrival per epilogue warp of every CTA
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
+      // ===================== TMA producer (every CTA) =====================
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM;
-        const int n0 = (tile % num_n) * BN;
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        const int m0 = (tile / num_n) * MT + rank * BM;
+        const int n0 = (tile % num_n) * BN + rank * C::BN_LOAD;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
-          tma_load_2d(sA + s * C::A_BYTES, &tma_a, &full[s], kb * BK, m0);
-          tma_load_2d(sB + s * C::B_BYTES, &tma_b, &full[s], kb * BK, n0);
+          if constexpr (PAIR) {
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(sA + s * C::A_BYTES, &tma_a, lead_full, kb * BK, m0);
+            tma_load_2d_pair(sB + s * C::B_BYTES, &tma_b, lead_full, kb * BK, n0);
+            if (rank != 0) mbar_arrive_cluster(lead_full);
+          } else {
+            mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+            tma_load_2d(sA + s * C::A_BYTES, &tma_a, &full[s], kb * BK, m0);
+            tma_load_2d(sB + s * C::B_BYTES, &tma_b, &full[s], kb * BK, n0);
+          }
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -271,16 +370,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(MT, BN);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(&tempty[as], aph ^ 1);  // epilogue has drained this accumulator
+        mbar_wait(&tempty[as], aph ^ 1);  // epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * C::ACC_STRIDE;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -290,67 +389,112 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16_ss(tacc, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR)
+              umma_bf16_ss_pair(tacc, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(tacc, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty[s], 0x3); else umma_commit(&empty[s]);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogues of both CTAs
+        if constexpr (PAIR) umma_commit_pair(&tfull[as], 0x3); else umma_commit(&tfull[as]);
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (every CTA, its own 128 rows) =====================
     const int q = warp & 3;         // TMEM lane quadrant this warp may access
     const int g = (warp - 4) >> 2;  // column group
+    const uint32_t stg = smem_u32(sStg) + (warp - 4) * C::STG_WARP;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / num_n) * BM;
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      const int m0 = (tile / num_n) * MT + rank * BM;
       const int n0 = (tile % num_n) * BN;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16) + g * CW;
-      epilogue_tile<EPI, CW>(taddr, m0 + q * 32 + lane, n0 + g * CW, p);
+      epilogue_tile<EPI, CW>(taddr, m0 + q * 32, lane, n0 + g * CW, p, &tma_out, stg);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+        else mbar_arrive(&tempty[as]);
+      }
     }
+    if (epi_stage_bytes(EPI) > 0 && lane == 0) bulk_wait<0>();  // all TMA stores / reductions have landed
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int BN, int EG, int EPI>
-int launch_one(const b200vit_gemm_args& a, cudaStream_t stream) {
-  using C = TileCfg<BN>;
-  CUtensorMap ta, tb;
+bool use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VIT_GEMM_PAIR");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int BN, int EG, int EPI, bool PAIR>
+int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream) {
+  using C = TileCfg<BN, EG, EPI, PAIR>;
+  constexpr int MT = PAIR ? 2 * BM : BM;
+  CUtensorMap ta, tb, to;
   int rc = make_tmap_bf16(&ta, a.d_a, a.m, a.k, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, a.d_b, a.n, a.k, BN);
+  rc = make_tmap_bf16(&tb, a.d_b, a.n, a.k, C::BN_LOAD);
   if (rc) return rc;
-  GemmParams p{a.d_out, a.d_bias, a.d_row_map, a.d_cos, a.d_sin, a.m, a.n, a.k, a.ldo, a.rope_cols};
-  auto kern = gemm_tcgen05_kernel<BN, EG, EPI>;
+  to = ta;
+  if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, false);
+  else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, true);
+  else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, true);
+  else if (EPI == B200VIT_EPI_BIAS_GELU) rc = make_tmap_2d(&to, a.d_out, a.m, a.n, a.ldo, 2, 32, 64, true);
+  if (rc) return rc;
+  GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const uint32_t*>(a.d_rope), a.m, a.n, a.k, a.ldo, a.rope_cols};
+  auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int num_tiles = ((a.m + BM - 1) / BM) * ((a.n + BN - 1) / BN);
+  const int num_tiles = ((a.m + MT - 1) / MT) * ((a.n + BN - 1) / BN);
   const int sms = device_sm_count();
-  const int grid = num_tiles < sms ? num_tiles : sms;
-  kern<<<grid, 128 + 128 * EG, C::SMEM_BYTES, stream>>>(ta, tb, p);
-  B200_CUDA_OK(cudaGetLastError());
+  const int max_units = PAIR ? sms / 2 : sms;
+  const int units = num_tiles < max_units ? num_tiles : max_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(PAIR ? 2 * units : units);
+  cfg.blockDim = dim3(128 + 128 * EG);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, p));
   return 0;
+}
+
+template <int BN, int EG, int EPI>
+int launch_one(const b200vit_gemm_args& a, cudaStream_t stream) {
+  if (use_pair()) return launch_cfg<BN, EG, EPI, true>(a, stream);
+  return launch_cfg<BN, EG, EPI, false>(a, stream);
 }
 
 }  // namespace
@@ -370,8 +514,8 @@ int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream) {
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
       return launch_one<256, 2, B200VIT_EPI_BIAS_F32>(a, stream);
     case B200VIT_EPI_QKV_ROPE:
-      if (a.n % 240 || a.rope_cols % 80 || a.ldo % 8 || !a.d_cos || !a.d_sin)
-        return fail(B200VIT_EINVAL, "gemm: QKV epilogue needs N % 240 == 0, head_dim 80, cos/sin tables");
+      if (a.n % 240 || a.rope_cols % 80 || a.ldo % 8 || !a.d_rope)
+        return fail(B200VIT_EINVAL, "gemm: QKV epilogue needs N % 240 == 0, head_dim 80, a rope table");
       return launch_one<240, 3, B200VIT_EPI_QKV_ROPE>(a, stream);
     case B200VIT_EPI_BIAS_RESIDUAL:
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");

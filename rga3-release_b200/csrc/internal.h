@@ -26,6 +26,10 @@ int check_arch();  // 0 if the current device is sm_100, else B200VIT_EARCH
 // 2-D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], SWIZZLE_128B,
 // out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
+// General 2-D row-major map: elem_bytes 2 (bf16) or 4 (fp32), row pitch `pitch_elems`, box = [box_rows, box_cols],
+// swizzle128 = SWIZZLE_128B (box_cols * elem_bytes must be 128) or no swizzle.
+int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int elem_bytes,
+                 int box_rows, int box_cols, bool swizzle128);
 
 // kernels (all enqueue on `stream`, no host sync)
 int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream);

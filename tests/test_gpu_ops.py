@@ -19,13 +19,17 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_gemm(a, b, epi, out, bias=None, row_map=None, cos=None, sin=None, ldo=None, rope_cols=0):
+def pack_rope(cos, sin):
+    """[M,40] fp32 cos / sin -> [M,40] fp16 (cos, sin) pairs viewed as int32 (what the QKV epilogue reads)."""
+    return torch.stack([cos.to(torch.float16), sin.to(torch.float16)], dim=-1).contiguous().view(torch.int32).reshape(cos.shape)
+
+
+def run_gemm(a, b, epi, out, bias=None, row_map=None, rope=None, ldo=None, rope_cols=0):
     g = _lib.GemmArgs()
     g.d_a, g.d_b, g.d_out = a.data_ptr(), b.data_ptr(), out.data_ptr()
     g.d_bias = bias.data_ptr() if bias is not None else None
     g.d_row_map = row_map.data_ptr() if row_map is not None else None
-    g.d_cos = cos.data_ptr() if cos is not None else None
-    g.d_sin = sin.data_ptr() if sin is not None else None
+    g.d_rope = rope.data_ptr() if rope is not None else None
     g.m, g.k = a.shape
     g.n = b.shape[0]
     g.ldo = ldo if ldo is not None else out.shape[1]
@@ -76,7 +80,7 @@ def test_gemm_qkv_rope(m, d):
     ang = rnd((m, 40), 7, 3.0, torch.float32)
     cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
     out = torch.zeros(m, 3 * d, dtype=torch.bfloat16, device=DEV)
-    run_gemm(a, b, _lib.EPI_QKV_ROPE, out, bias=bias, cos=cos, sin=sin, rope_cols=2 * d)
+    run_gemm(a, b, _lib.EPI_QKV_ROPE, out, bias=bias, rope=pack_rope(cos, sin), rope_cols=2 * d)
     qkv = (a.float() @ b.float().t() + bias).cpu().reshape(m, 3, nh, 80)
     c80 = torch.cat([cos, cos], -1).cpu()
     s80 = torch.cat([sin, sin], -1).cpu()

@@ -44,13 +44,12 @@ def gemm_fn(m, n, k, epi, ldo=None, rope=False, out_dtype=torch.bfloat16):
     bias = torch.randn(n, device=DEV)
     ocols = ldo if ldo else n
     out = torch.zeros(m, ocols, dtype=out_dtype, device=DEV)
-    cos = torch.rand(m, 40, device=DEV)
-    sin = torch.rand(m, 40, device=DEV)
+    rope_t = torch.randint(0, 2 ** 30, (m, 40), dtype=torch.int32, device=DEV) & 0x3BFF3BFF  # finite fp16 pairs
     g = _lib.GemmArgs()
     g.d_a, g.d_b, g.d_out, g.d_bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr()
-    g.d_cos, g.d_sin = cos.data_ptr(), sin.data_ptr()
+    g.d_rope = rope_t.data_ptr()
     g.m, g.n, g.k, g.ldo, g.rope_cols, g.epilogue = m, n, k, ocols, (2 * n // 3 if rope else 0), epi
-    keep = (a, b, bias, out, cos, sin)
+    keep = (a, b, bias, out, rope_t)
 
     def fn():
         _lib.check(_lib.lib().b200vit_gemm(C.byref(g), stream()), "gemm")
