@@ -39,6 +39,7 @@ struct GemmParams {
   const int32_t* row_map;
   const uint32_t* rope;  // [M, 40] half2 (cos, sin)
   int m, n, k, ldo, rope_cols;
+  int stream_k;  // 1: stream-K decomposition (BIAS_RESIDUAL only)
 };
 
 // staging bytes per epilogue warp (TMA-store epilogues), 0 = direct global stores
@@ -87,7 +88,7 @@ __device__ __forceinline__ uint32_t swz128(uint32_t base, int lane, int j) {
 // `stg` = this warp's staging buffer (shared address), `row0` = first row of the warp's 32-row slab.
 template <int EPI, int CW>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane, int col0, const GemmParams& p,
-                                              const CUtensorMap* tma_out, uint32_t stg) {
+                                              const CUtensorMap* tma_out, uint32_t stg, bool first_split) {
   const int row = row0 + lane;
   const bool row_ok = row < p.m;
   if constexpr (EPI == B200VIT_EPI_QKV_ROPE) {
@@ -161,7 +162,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 b = bias4(p.bias, col + 4 * j, p.n);
+        // a tile completed by several stream-K partials gets the bias from the split that holds k = 0
+        const float4 b = first_split ? bias4(p.bias, col + 4 * j, p.n) : make_float4(0.f, 0.f, 0.f, 0.f);
         st_shared_v4(swz128(buf, lane, j), __float_as_uint(__uint_as_float(v[4 * j]) + b.x),
                      __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y),
                      __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z),
@@ -277,6 +279,55 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
   }
 }
 
+// ------------------------------------------------------------------ work decomposition
+// A "segment" is a contiguous range of k-blocks of one output tile.  Data-parallel mode: unit u
+// takes whole tiles u, u + U, ...  Stream-K mode (reduce-add epilogues only): the flattened
+// (tile, k-block) space is cut into U equal ranges, so all CTA pairs finish together even when
+// the tile count is a poor multiple of the pair count (N = 1280 at M = 8192: 160 tiles on 74
+// pairs); tiles cut by a range boundary are completed by several partial reduce-adds.
+struct Segment {
+  int tile, kb0, kb1;
+};
+struct WorkIter {
+  int num_tiles, num_kb, unit, num_units;
+  bool stream_k;
+  int tile;               // data-parallel cursor
+  long long pos, end;     // stream-K cursor in k-block units
+  __device__ WorkIter(int num_tiles_, int num_kb_, int unit_, int num_units_, bool stream_k_)
+      : num_tiles(num_tiles_), num_kb(num_kb_), unit(unit_), num_units(num_units_), stream_k(stream_k_), tile(unit_) {
+    if (stream_k) {
+      pos = boundary(unit);
+      end = boundary(unit + 1);
+    }
+  }
+  // range boundary of unit u, snapped to a tile boundary when it would leave a sliver (< 4 k-blocks)
+  __device__ long long boundary(int u) const {
+    const long long total = static_cast<long long>(num_tiles) * num_kb;
+    if (u >= num_units) return total;
+    long long b = total * u / num_units;
+    const int r = static_cast<int>(b % num_kb);
+    if (r < 4) b -= r;
+    else if (r > num_kb - 4) b += num_kb - r;
+    return b;
+  }
+  __device__ bool next(Segment& s) {
+    if (!stream_k) {
+      if (tile >= num_tiles) return false;
+      s.tile = tile, s.kb0 = 0, s.kb1 = num_kb;
+      tile += num_units;
+      return true;
+    }
+    if (pos >= end) return false;
+    s.tile = static_cast<int>(pos / num_kb);
+    s.kb0 = static_cast<int>(pos % num_kb);
+    const long long tile_end = static_cast<long long>(s.tile + 1) * num_kb;
+    const long long e = end < tile_end ? end : tile_end;
+    s.kb1 = s.kb0 + static_cast<int>(e - pos);
+    pos = e;
+    return true;
+  }
+};
+
 // ------------------------------------------------------------------ kernel
 template <int BN, int EG, int EPI, bool PAIR>
 __global__ void __launch_bounds__(128 + 128 * EG, 1)
@@ -346,10 +397,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // ===================== TMA producer (every CTA) =====================
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
-        const int m0 = (tile / num_n) * MT + rank * BM;
-        const int n0 = (tile % num_n) * BN + rank * C::BN_LOAD;
-        for (int kb = 0; kb < num_kb; ++kb) {
+      WorkIter work(num_tiles, num_kb, unit, num_units, p.stream_k != 0);
+      Segment sg;
+      while (work.next(sg)) {
+        const int m0 = (sg.tile / num_n) * MT + rank * BM;
+        const int n0 = (sg.tile % num_n) * BN + rank * C::BN_LOAD;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           if constexpr (PAIR) {
             const uint32_t lead_full = mapa_u32(smem_u32(&full[s]), 0);
@@ -376,13 +429,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      WorkIter work(num_tiles, num_kb, unit, num_units, p.stream_k != 0);
+      Segment sg;
+      for (; work.next(sg); ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);  // epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * C::ACC_STRIDE;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * C::A_BYTES);
@@ -391,10 +446,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int k = 0; k < BK / 16; ++k) {
             if constexpr (PAIR)
               umma_bf16_ss_pair(tacc, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                                (kb | k) != 0 ? 1u : 0u);
+                                (kb != sg.kb0 || k != 0) ? 1u : 0u);
             else
               umma_bf16_ss(tacc, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+                           (kb != sg.kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs) when these MMAs retire
           if constexpr (PAIR) umma_commit_pair(&empty[s], 0x3); else umma_commit(&empty[s]);
@@ -413,15 +468,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int g = (warp - 4) >> 2;  // column group
     const uint32_t stg = smem_u32(sStg) + (warp - 4) * C::STG_WARP;
     int it = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
-      const int m0 = (tile / num_n) * MT + rank * BM;
-      const int n0 = (tile % num_n) * BN;
+    WorkIter work(num_tiles, num_kb, unit, num_units, p.stream_k != 0);
+    Segment sg;
+    for (; work.next(sg); ++it) {
+      const int m0 = (sg.tile / num_n) * MT + rank * BM;
+      const int n0 = (sg.tile % num_n) * BN;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16) + g * CW;
-      epilogue_tile<EPI, CW>(taddr, m0 + q * 32, lane, n0 + g * CW, p, &tma_out, stg);
+      epilogue_tile<EPI, CW>(taddr, m0 + q * 32, lane, n0 + g * CW, p, &tma_out, stg, sg.kb0 == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -438,6 +495,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+bool stream_k_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VIT_STREAM_K");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 bool use_pair() {
@@ -464,7 +530,7 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream) {
   else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, true);
   else if (EPI == B200VIT_EPI_BIAS_GELU) rc = make_tmap_2d(&to, a.d_out, a.m, a.n, a.ldo, 2, 32, 64, true);
   if (rc) return rc;
-  GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const uint32_t*>(a.d_rope), a.m, a.n, a.k, a.ldo, a.rope_cols};
+  GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const uint32_t*>(a.d_rope), a.m, a.n, a.k, a.ldo, a.rope_cols, 0};
   auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -474,7 +540,16 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream) {
   const int num_tiles = ((a.m + MT - 1) / MT) * ((a.n + BN - 1) / BN);
   const int sms = device_sm_count();
   const int max_units = PAIR ? sms / 2 : sms;
-  const int units = num_tiles < max_units ? num_tiles : max_units;
+  int units = num_tiles < max_units ? num_tiles : max_units;
+  if (EPI == B200VIT_EPI_BIAS_RESIDUAL && stream_k_enabled()) {
+    // reduce-add epilogue: partial tiles simply add, so balance the k-blocks over all pairs when the
+    // tile count is not a multiple of the pair count (and each pair still gets >= 8 k-blocks)
+    const long long total = static_cast<long long>(num_tiles) * ((a.k + BK - 1) / BK);
+    if (num_tiles % max_units != 0 && total / max_units >= 8) {
+      units = max_units;
+      p.stream_k = 1;
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(PAIR ? 2 * units : units);
   cfg.blockDim = dim3(128 + 128 * EG);
