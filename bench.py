@@ -233,7 +233,7 @@ def main():
     def step_resident():
         tower.forward_frames(frames_dev, overlay, out=out)
         if world > 1:
-            dist.gather(out, gather_list, dst=0)
+            dist.gather(out, gather_list, dst=0)  # merged tokens -> LLM rank (NCCL over NVLink)
 
     def barrier():
         torch.cuda.synchronize(dev)
