@@ -107,46 +107,61 @@ def random_state_dict_gpu(tower, seed=0):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / power / throttle reasons DURING the timed region, read in-process through NVML
+    (nvidia_ml_py) every 50 ms; falls back to one `nvidia-smi` query per sample if NVML is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index, interval=0.1):
+        self.idx, self.rows, self.stop_flag, self.thread, self.h = gpu_index, [], False, None, None
+        self.interval = interval   # NVML queries perturb the GPU for ~ms: a handful of samples per region, not a stream
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            nv, h = self.nv, self.h
+            try:
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            return (nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                    nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons))
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        o = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        return float(o[0]), float(o[1]), float(o[2]), int(o[3].strip(), 16)
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.time(),) + tuple(self._sample()))
+            except Exception:
+                pass
+            time.sleep(self.interval)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, pw = [], None, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                mx = float(f[1])
-                if t0 - 0.05 <= ts <= t1 + 0.15:
-                    sm.append(float(f[0]))
-                    pw.append(float(f[2]))
-                    for n, v in zip(names, f[3:7]):
-                        if v.lower().startswith("active"):
-                            reasons.add(n)
-            except ValueError:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-1:]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        bits = 0
+        for r in rows:
+            bits |= r[4]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(rows[0][2]),
+                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(rows),
+                "power_w_max": float(max(r[3] for r in rows)), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- reference (CPU) arm
@@ -230,10 +245,22 @@ def main():
     out = torch.empty(m // 4, CFG_7B["out_hidden_size"], dtype=torch.bfloat16, device=dev)
     gather_list = [torch.empty_like(out) for _ in range(world)] if (world > 1 and rank == 0) else None
 
+    do_gather = world > 1 and not os.environ.get("BENCH_NO_GATHER")
+    gmode = os.environ.get("BENCH_GATHER", "gather")
+    ag_buf = torch.empty(world * out.shape[0], out.shape[1], dtype=out.dtype, device=dev) if world > 1 else None
+
+    def gather_out(t):
+        if gmode == "gather":
+            dist.gather(t, gather_list, dst=0)  # merged tokens -> LLM rank (NCCL over NVLink)
+        elif gmode == "p2p":
+            vit.gather_tokens(t, [t.shape[0]] * world, dst=0)
+        else:
+            dist.all_gather_into_tensor(ag_buf, t)
+
     def step_resident():
         tower.forward_frames(frames_dev, overlay, out=out)
-        if world > 1:
-            dist.gather(out, gather_list, dst=0)  # merged tokens -> LLM rank (NCCL over NVLink)
+        if do_gather:
+            gather_out(out)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -242,13 +269,18 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- resident-input timing
-    for _ in range(args.warmup):
+    for _ in range(args.warmup - 1):
         step_resident()
+    torch.cuda.synchronize(dev)
+    t_w = time.perf_counter()
+    step_resident()
+    torch.cuda.synchronize(dev)
+    est_total = (time.perf_counter() - t_w) * args.steps
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, interval=min(max(est_total / 5.0, 0.1), 1.0))
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.1)
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -262,6 +294,13 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- host cost of enqueueing one step: two steps into an empty queue (no back-pressure from the GPU)
+    t_h = time.perf_counter()
+    for _ in range(2):
+        tower.forward_frames(frames_dev, overlay, out=out)
+    host_ms = (time.perf_counter() - t_h) * 1e3 / 2
+    torch.cuda.synchronize(dev)
 
     # ---- per-kernel breakdown (cudaEvent pairs around every launch; separate pass over the same K steps)
     tower.profile(grid, True)
@@ -296,8 +335,8 @@ def main():
             if ev_d[b] is not None:
                 cur.wait_event(ev_d[b])                # D2H of step i-2 has drained this output buffer
             tower.forward_frames(fr_dev[b], overlay, out=out_dev[b])
-            if world > 1:
-                dist.gather(out_dev[b], gather_list, dst=0)
+            if do_gather:
+                gather_out(out_dev[b])
             ev_c[b] = torch.cuda.Event()
             ev_c[b].record(cur)
             with torch.cuda.stream(s_d2h):
@@ -349,7 +388,7 @@ def main():
             "e2e": {"value": frames_total / (e2e_ms_total * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": int(out.numel() * out.element_size()),
                     "ms_per_step": e2e_ms_total / args.steps},
-            "gpu_launches": launches * args.steps,
+            "gpu_launches": launches * args.steps, "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
                          "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",

@@ -28,13 +28,14 @@ struct b200vit_plan {
   size_t off_x = 0, off_h = 0, off_qkv = 0, off_attn = 0, off_act = 0, off_pv = 0, ws_bytes = 0;
   int ipad = 0, kpe = 0;
   // device copies (lazy)
-  std::mutex mu;
+  std::mutex mu, fwd_mu;
   bool uploaded = false;
   int32_t* d_row_map = nullptr;
   int32_t* d_merge_map = nullptr;
   uint32_t* d_rope = nullptr;
   AttnWork* d_work_window = nullptr;
   AttnWork* d_work_full = nullptr;
+  std::vector<GemmPrepared> gemm_cache;   // one memo per GEMM call site of forward()
   // optional per-launch profiling (cudaEvent pairs around every launch of a forward)
   bool profile = false;
   std::vector<cudaEvent_t> ev;       // 2 per launch
@@ -306,6 +307,9 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
   void* act = ws + p->off_act;
   void* pv = ws + p->off_pv;
 
+  std::lock_guard<std::mutex> fwd_lock(p->fwd_mu);   // call-site memos and event lists are per plan
+  if (p->gemm_cache.size() != static_cast<size_t>(3 + 4 * c.depth)) p->gemm_cache.assign(3 + 4 * c.depth, GemmPrepared());
+  int site = 0;
   Prof prof{p, stream};
   p->ev_used = 0;
   const void* a0 = d_pixel_values;
@@ -326,7 +330,7 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
   g.d_a = a0, g.d_b = w->patch_w, g.d_out = x, g.d_row_map = p->d_row_map;
   g.m = M, g.n = D, g.k = p->kpe, g.ldo = D, g.epilogue = B200VIT_EPI_STORE_F32;
   prof.begin(B200VIT_K_PATCH_EMBED);
-  if ((rc = launch_gemm(g, stream))) return rc;
+  if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
   prof.end();
 
   for (int l = 0; l < c.depth; ++l) {
@@ -339,7 +343,7 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     g.d_a = h, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_rope = p->d_rope;
     g.m = M, g.n = 3 * D, g.k = D, g.ldo = 3 * D, g.rope_cols = 2 * D, g.epilogue = B200VIT_EPI_QKV_ROPE;
     prof.begin(B200VIT_K_QKV);
-    if ((rc = launch_gemm(g, stream))) return rc;
+    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
     prof.end();
     prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
     if ((rc = launch_attention(qkv, attn, full ? p->d_work_full : p->d_work_window,
@@ -350,7 +354,7 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     g.d_a = attn, g.d_b = lw.proj_w, g.d_out = x, g.d_bias = lw.proj_b;
     g.m = M, g.n = D, g.k = D, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
     prof.begin(B200VIT_K_PROJ);
-    if ((rc = launch_gemm(g, stream))) return rc;
+    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
     prof.end();
     prof.begin(B200VIT_K_RMSNORM);
     if ((rc = launch_rmsnorm(x, lw.norm2_w, h, M, D, 1e-6f, stream))) return rc;
@@ -359,13 +363,13 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     g.d_a = h, g.d_b = lw.gateup_w, g.d_out = act, g.d_bias = lw.gateup_b;
     g.m = M, g.n = 2 * p->ipad, g.k = D, g.ldo = p->ipad, g.epilogue = B200VIT_EPI_SWIGLU;
     prof.begin(B200VIT_K_GATEUP);
-    if ((rc = launch_gemm(g, stream))) return rc;
+    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
     prof.end();
     std::memset(&g, 0, sizeof(g));
     g.d_a = act, g.d_b = lw.down_w, g.d_out = x, g.d_bias = lw.down_b;
     g.m = M, g.n = D, g.k = p->ipad, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
     prof.begin(B200VIT_K_DOWN);
-    if ((rc = launch_gemm(g, stream))) return rc;
+    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
     prof.end();
   }
   if (d_last_hidden)
@@ -379,14 +383,14 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
   g.d_a = h, g.d_b = w->merger_fc1_w, g.d_out = attn, g.d_bias = w->merger_fc1_b;
   g.m = Mm, g.n = Dm, g.k = Dm, g.ldo = Dm, g.epilogue = B200VIT_EPI_BIAS_GELU;
   prof.begin(B200VIT_K_MERGER_FC1);
-  if ((rc = launch_gemm(g, stream))) return rc;
+  if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
   prof.end();
   std::memset(&g, 0, sizeof(g));
   g.d_a = attn, g.d_b = w->merger_fc2_w, g.d_out = d_out, g.d_bias = w->merger_fc2_b, g.d_row_map = p->d_merge_map;
   g.m = Mm, g.n = c.out_hidden, g.k = Dm, g.ldo = c.out_hidden;
   g.epilogue = out_f32 ? B200VIT_EPI_BIAS_F32 : B200VIT_EPI_BIAS_BF16;
   prof.begin(B200VIT_K_MERGER_FC2);
-  if ((rc = launch_gemm(g, stream))) return rc;
+  if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
   prof.end();
   return 0;
 }

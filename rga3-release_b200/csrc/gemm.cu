@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -516,42 +517,51 @@ bool use_pair() {
 }
 
 template <int BN, int EG, int EPI, bool PAIR>
-int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream) {
+int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* cache) {
   using C = TileCfg<BN, EG, EPI, PAIR>;
   constexpr int MT = PAIR ? 2 * BM : BM;
-  CUtensorMap ta, tb, to;
-  int rc = make_tmap_bf16(&ta, a.d_a, a.m, a.k, BM);
-  if (rc) return rc;
-  rc = make_tmap_bf16(&tb, a.d_b, a.n, a.k, C::BN_LOAD);
-  if (rc) return rc;
-  to = ta;
-  if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, false);
-  else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, true);
-  else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, true);
-  else if (EPI == B200VIT_EPI_BIAS_GELU) rc = make_tmap_2d(&to, a.d_out, a.m, a.n, a.ldo, 2, 32, 64, true);
-  if (rc) return rc;
-  GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const uint32_t*>(a.d_rope), a.m, a.n, a.k, a.ldo, a.rope_cols, 0};
+  GemmPrepared local;
+  GemmPrepared& g = cache ? *cache : local;
+  if (!(g.valid && std::memcmp(&g.key, &a, sizeof(a)) == 0)) {
+    g.valid = false;
+    int rc = make_tmap_bf16(&g.ta, a.d_a, a.m, a.k, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&g.tb, a.d_b, a.n, a.k, C::BN_LOAD);
+    if (rc) return rc;
+    g.to = g.ta;
+    if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, false);
+    else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, true);
+    else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, true);
+    else if (EPI == B200VIT_EPI_BIAS_GELU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 64, true);
+    if (rc) return rc;
+    const int num_tiles = ((a.m + MT - 1) / MT) * ((a.n + BN - 1) / BN);
+    const int sms = device_sm_count();
+    const int max_units = PAIR ? sms / 2 : sms;
+    int units = num_tiles < max_units ? num_tiles : max_units;
+    g.stream_k = 0;
+    if (EPI == B200VIT_EPI_BIAS_RESIDUAL && stream_k_enabled()) {
+      // reduce-add epilogue: partial tiles simply add, so balance the k-blocks over all pairs when the
+      // tile count is not a multiple of the pair count (and each pair still gets >= 8 k-blocks)
+      const long long total = static_cast<long long>(num_tiles) * ((a.k + BK - 1) / BK);
+      if (num_tiles % max_units != 0 && total / max_units >= 8) {
+        units = max_units;
+        g.stream_k = 1;
+      }
+    }
+    g.grid = PAIR ? 2 * units : units;
+    g.key = a;
+    g.valid = true;
+  }
+  GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const uint32_t*>(a.d_rope), a.m, a.n, a.k, a.ldo,
+               a.rope_cols, g.stream_k};
   auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int num_tiles = ((a.m + MT - 1) / MT) * ((a.n + BN - 1) / BN);
-  const int sms = device_sm_count();
-  const int max_units = PAIR ? sms / 2 : sms;
-  int units = num_tiles < max_units ? num_tiles : max_units;
-  if (EPI == B200VIT_EPI_BIAS_RESIDUAL && stream_k_enabled()) {
-    // reduce-add epilogue: partial tiles simply add, so balance the k-blocks over all pairs when the
-    // tile count is not a multiple of the pair count (and each pair still gets >= 8 k-blocks)
-    const long long total = static_cast<long long>(num_tiles) * ((a.k + BK - 1) / BK);
-    if (num_tiles % max_units != 0 && total / max_units >= 8) {
-      units = max_units;
-      p.stream_k = 1;
-    }
-  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(PAIR ? 2 * units : units);
+  cfg.gridDim = dim3(g.grid);
   cfg.blockDim = dim3(128 + 128 * EG);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
@@ -562,19 +572,19 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, p));
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.ta, g.tb, g.to, p));
   return 0;
 }
 
 template <int BN, int EG, int EPI>
-int launch_one(const b200vit_gemm_args& a, cudaStream_t stream) {
-  if (use_pair()) return launch_cfg<BN, EG, EPI, true>(a, stream);
-  return launch_cfg<BN, EG, EPI, false>(a, stream);
+int launch_one(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* cache) {
+  if (use_pair()) return launch_cfg<BN, EG, EPI, true>(a, stream, cache);
+  return launch_cfg<BN, EG, EPI, false>(a, stream, cache);
 }
 
 }  // namespace
 
-int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream) {
+int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* cache) {
   if (a.m <= 0 || a.n <= 0 || a.k <= 0) return fail(B200VIT_EINVAL, "gemm: empty problem");
   if (a.k % 8 != 0) return fail(B200VIT_EINVAL, "gemm: K must be a multiple of 8 (16-byte rows for TMA)");
   if ((reinterpret_cast<uintptr_t>(a.d_a) | reinterpret_cast<uintptr_t>(a.d_b) | reinterpret_cast<uintptr_t>(a.d_out)) & 15)
@@ -584,26 +594,26 @@ int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream) {
   switch (a.epilogue) {
     case B200VIT_EPI_STORE_F32:
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
-      return launch_one<256, 2, B200VIT_EPI_STORE_F32>(a, stream);
+      return launch_one<256, 2, B200VIT_EPI_STORE_F32>(a, stream, cache);
     case B200VIT_EPI_BIAS_F32:
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
-      return launch_one<256, 2, B200VIT_EPI_BIAS_F32>(a, stream);
+      return launch_one<256, 2, B200VIT_EPI_BIAS_F32>(a, stream, cache);
     case B200VIT_EPI_QKV_ROPE:
       if (a.n % 240 || a.rope_cols % 80 || a.ldo % 8 || !a.d_rope)
         return fail(B200VIT_EINVAL, "gemm: QKV epilogue needs N % 240 == 0, head_dim 80, a rope table");
-      return launch_one<240, 3, B200VIT_EPI_QKV_ROPE>(a, stream);
+      return launch_one<240, 3, B200VIT_EPI_QKV_ROPE>(a, stream, cache);
     case B200VIT_EPI_BIAS_RESIDUAL:
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
-      return launch_one<256, 2, B200VIT_EPI_BIAS_RESIDUAL>(a, stream);
+      return launch_one<256, 2, B200VIT_EPI_BIAS_RESIDUAL>(a, stream, cache);
     case B200VIT_EPI_SWIGLU:
       if (a.n % 16 || a.ldo % 8) return fail(B200VIT_EINVAL, "gemm: SwiGLU needs N % 16 == 0 and ldo % 8 == 0");
-      return launch_one<256, 2, B200VIT_EPI_SWIGLU>(a, stream);
+      return launch_one<256, 2, B200VIT_EPI_SWIGLU>(a, stream, cache);
     case B200VIT_EPI_BIAS_GELU:
       if (a.n % 8 || a.ldo % 8) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 8 required");
-      return launch_one<256, 2, B200VIT_EPI_BIAS_GELU>(a, stream);
+      return launch_one<256, 2, B200VIT_EPI_BIAS_GELU>(a, stream, cache);
     case B200VIT_EPI_BIAS_BF16:
       if (a.n % 8 || a.ldo % 8) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 8 required");
-      return launch_one<256, 2, B200VIT_EPI_BIAS_BF16>(a, stream);
+      return launch_one<256, 2, B200VIT_EPI_BIAS_BF16>(a, stream, cache);
     default:
       return fail(B200VIT_EINVAL, "gemm: unknown epilogue");
   }

@@ -32,7 +32,15 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols,
                  int box_rows, int box_cols, bool swizzle128);
 
 // kernels (all enqueue on `stream`, no host sync)
-int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream);
+// Host-side memo of one GEMM call site: tensor maps and launch geometry are rebuilt only when the
+// arguments change (cuTensorMapEncodeTiled x3 per launch made the host the bottleneck otherwise).
+struct GemmPrepared {
+  bool valid = false;
+  b200vit_gemm_args key;
+  CUtensorMap ta, tb, to;
+  int grid = 0, stream_k = 0;
+};
+int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* cache = nullptr);
 int launch_rmsnorm(const float* x, const float* w, void* out_bf16, int rows, int dim, float eps, cudaStream_t stream);
 int launch_cast_bf16(const void* in, int in_dtype, void* out, int64_t n, cudaStream_t stream);
 
