@@ -2,7 +2,9 @@
 // single-op entry points.  See include/b200vit.h for the contract.
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -23,7 +25,11 @@ struct b200vit_plan {
   std::vector<int32_t> cu_window, cu_full, row_map, merge_map, pos_ids;
   std::vector<float> rope_cos, rope_sin;  // [M, head_dim/2] in window order
   std::vector<uint32_t> rope_packed;      // same table as fp16 (cos, sin) pairs -- what the QKV epilogue reads
-  std::vector<AttnWork> work_window, work_full;
+  std::vector<AttnWork> work_window, work_full;          // legacy mma.sync attention
+  std::vector<AttnTile> tiles_window, tiles_full;         // tcgen05 attention
+  std::vector<int32_t> bounds_window, bounds_full;        // per-row [lo, hi) of the row's segment
+  int maxblk_window = 0, maxblk_full = 0;
+  AttnPrepared attn_cache;
   // workspace layout (byte offsets)
   size_t off_x = 0, off_h = 0, off_qkv = 0, off_attn = 0, off_act = 0, off_pv = 0, ws_bytes = 0;
   int ipad = 0, kpe = 0;
@@ -35,6 +41,10 @@ struct b200vit_plan {
   uint32_t* d_rope = nullptr;
   AttnWork* d_work_window = nullptr;
   AttnWork* d_work_full = nullptr;
+  AttnTile* d_tiles_window = nullptr;
+  AttnTile* d_tiles_full = nullptr;
+  int32_t* d_bounds_window = nullptr;
+  int32_t* d_bounds_full = nullptr;
   std::vector<GemmPrepared> gemm_cache;   // one memo per GEMM call site of forward()
   // optional per-launch profiling (cudaEvent pairs around every launch of a forward)
   bool profile = false;
@@ -145,6 +155,10 @@ int ensure_uploaded(b200vit_plan* p) {
   if ((rc = upload(&p->d_rope, p->rope_packed))) return rc;
   if ((rc = upload(&p->d_work_window, p->work_window))) return rc;
   if ((rc = upload(&p->d_work_full, p->work_full))) return rc;
+  if ((rc = upload(&p->d_tiles_window, p->tiles_window))) return rc;
+  if ((rc = upload(&p->d_tiles_full, p->tiles_full))) return rc;
+  if ((rc = upload(&p->d_bounds_window, p->bounds_window))) return rc;
+  if ((rc = upload(&p->d_bounds_full, p->bounds_full))) return rc;
   p->uploaded = true;
   return 0;
 }
@@ -173,6 +187,15 @@ struct Prof {
     p->ev_used += 2;
   }
 };
+
+bool legacy_attention() {  // B200VIT_ATTN=legacy selects the mma.sync kernel (A/B comparison only)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VIT_ATTN");
+    v = (e != nullptr && std::strcmp(e, "legacy") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
 
 bool is_fullatt(const b200vit_cfg& c, int layer) {
   for (int i = 0; i < c.n_fullatt; ++i)
@@ -228,6 +251,10 @@ int b200vit_plan_create(const int64_t* h_grid_thw, int n_grids, const b200vit_cf
   build_rope(*p);
   build_work(p->cu_window, p->work_window);
   build_work(p->cu_full, p->work_full);
+  build_attn_tiles(p->cu_window, static_cast<int>(p->m), 128, p->tiles_window, p->bounds_window);
+  build_attn_tiles(p->cu_full, static_cast<int>(p->m), 256, p->tiles_full, p->bounds_full);
+  for (const AttnTile& t : p->tiles_window) p->maxblk_window = std::max(p->maxblk_window, t.n_kv_blocks);
+  for (const AttnTile& t : p->tiles_full) p->maxblk_full = std::max(p->maxblk_full, t.n_kv_blocks);
   // workspace
   p->ipad = static_cast<int>(align_up(c.intermediate, 128));
   p->kpe = c.in_channels * c.temporal_patch * c.patch * c.patch;
@@ -251,6 +278,10 @@ void b200vit_plan_destroy(b200vit_plan* p) {
   cudaFree(p->d_rope);
   cudaFree(p->d_work_window);
   cudaFree(p->d_work_full);
+  cudaFree(p->d_tiles_window);
+  cudaFree(p->d_tiles_full);
+  cudaFree(p->d_bounds_window);
+  cudaFree(p->d_bounds_full);
   for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
   delete p;
 }
@@ -346,9 +377,15 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
     prof.end();
     prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
-    if ((rc = launch_attention(qkv, attn, full ? p->d_work_full : p->d_work_window,
-                               static_cast<int>(full ? p->work_full.size() : p->work_window.size()), c.heads, stream)))
-      return rc;
+    if (legacy_attention())
+      rc = launch_attention(qkv, attn, full ? p->d_work_full : p->d_work_window,
+                            static_cast<int>(full ? p->work_full.size() : p->work_window.size()), c.heads, stream);
+    else
+      rc = launch_attention_tc(qkv, attn, full ? p->d_tiles_full : p->d_tiles_window,
+                               static_cast<int>(full ? p->tiles_full.size() : p->tiles_window.size()), full ? 256 : 128,
+                               full ? p->maxblk_full : p->maxblk_window, full ? p->d_bounds_full : p->d_bounds_window, M,
+                               c.heads, stream, &p->attn_cache);
+    if (rc) return rc;
     prof.end();
     std::memset(&g, 0, sizeof(g));
     g.d_a = attn, g.d_b = lw.proj_w, g.d_out = x, g.d_bias = lw.proj_b;
@@ -453,15 +490,39 @@ int b200vit_attention(const void* d_qkv, void* d_out, const int32_t* h_cu_seqlen
   if (rc) return rc;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   std::vector<int32_t> cu(h_cu_seqlens, h_cu_seqlens + n_segments + 1);
-  std::vector<AttnWork> work;
-  build_work(cu, work);
-  if (work.empty()) return 0;
-  AttnWork* d_work = nullptr;
-  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_work), work.size() * sizeof(AttnWork)));
-  B200_CUDA_OK(cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(AttnWork), cudaMemcpyHostToDevice, stream));
-  rc = launch_attention(d_qkv, d_out, d_work, static_cast<int>(work.size()), heads, stream);
-  cudaStreamSynchronize(stream);  // test entry point: the work list is freed before returning
-  cudaFree(d_work);
+  const int m_rows = cu.back();
+  if (legacy_attention()) {
+    std::vector<AttnWork> work;
+    build_work(cu, work);
+    if (work.empty()) return 0;
+    AttnWork* d_work = nullptr;
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_work), work.size() * sizeof(AttnWork)));
+    B200_CUDA_OK(cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(AttnWork), cudaMemcpyHostToDevice, stream));
+    rc = launch_attention(d_qkv, d_out, d_work, static_cast<int>(work.size()), heads, stream);
+    cudaStreamSynchronize(stream);  // test entry point: the work list is freed before returning
+    cudaFree(d_work);
+    return rc;
+  }
+  std::vector<AttnTile> tiles;
+  std::vector<int32_t> bounds;
+  int max_len = 0;
+  for (int i = 0; i < n_segments; ++i) max_len = std::max(max_len, cu[i + 1] - cu[i]);
+  const int rows_per_tile = max_len > 256 ? 256 : 128;  // long segments: two query tiles per CTA share K/V blocks
+  build_attn_tiles(cu, m_rows, rows_per_tile, tiles, bounds);
+  if (tiles.empty()) return 0;
+  int maxblk = 0;
+  for (const AttnTile& t : tiles) maxblk = std::max(maxblk, t.n_kv_blocks);
+  AttnTile* d_tiles = nullptr;
+  int32_t* d_bounds = nullptr;
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_tiles), tiles.size() * sizeof(AttnTile)));
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_bounds), bounds.size() * sizeof(int32_t)));
+  B200_CUDA_OK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(AttnTile), cudaMemcpyHostToDevice, stream));
+  B200_CUDA_OK(cudaMemcpyAsync(d_bounds, bounds.data(), bounds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  rc = launch_attention_tc(d_qkv, d_out, d_tiles, static_cast<int>(tiles.size()), rows_per_tile, maxblk, d_bounds, m_rows, heads,
+                           stream, nullptr);
+  cudaStreamSynchronize(stream);  // test entry point: the temporaries are freed before returning
+  cudaFree(d_tiles);
+  cudaFree(d_bounds);
   return rc;
 }
 

@@ -1,0 +1,446 @@
+// tcgen05 / TMEM varlen attention for head_dim 80 (Qwen2.5-VL vision tower, HF
+// modeling_qwen2_5_vl.py:244-283; softmax statistics in fp32 as :199).
+//
+// One CTA = QTILES x 128 consecutive query rows (window order) of one head.  Every row carries the
+// bounds [lo, hi) of its own cu_seqlens segment, so the same kernel serves
+//   * window layers (QTILES = 1): a 128-row tile holds two 64-patch windows (or several ragged edge
+//     windows); the K/V range is the union of their segments and the per-row bounds make the mask
+//     block-diagonal; 32-column chunks outside a row's segment are skipped;
+//   * full layers (QTILES = 2): 256 rows of one temporal slice (1024 / 2304 patches) share each
+//     128-row K/V block; the two query tiles ping-pong on the tensor core while the other tile's
+//     softmax runs (softmax is the bound: 128 exp2 per row per block on the 16/clk MUFU).
+// Per K/V block and query tile:
+//     S = Q K^T   (tcgen05.mma, TMA-loaded operands; head_dim 80 = a 64-wide SWIZZLE_128B sub-tile
+//                  + a 16-wide SWIZZLE_32B sub-tile, 5 MMAs of K = 16)
+//     P = exp2(S*scale - m)   thread-per-row from TMEM, bf16 into 128-B-swizzled smem
+//     O_blk = P V (tcgen05.mma; V in its natural [kv][d] layout as an MN-major B operand)
+//     o = o*alpha + O_blk      accumulated in registers (no TMEM rescale pass)
+// Warps: 0 = TMA loader, 1 = MMA issuer, 2.. = softmax/accumulate (4 per query tile; TMEM lane
+// quadrant = warp % 4).
+#include <cuda_bf16.h>
+
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int HD = 80;
+constexpr int QT = 128;   // query rows per tile
+constexpr int KVB = 128;  // kv rows per block
+constexpr int T64_BYTES = 128 * 128;  // [128 rows][64 cols] bf16
+constexpr int T16_BYTES = 128 * 32;   // [128 rows][16 cols] bf16
+constexpr int TILE_BYTES = T64_BYTES + T16_BYTES;
+constexpr int P_BYTES = 2 * T64_BYTES;  // [128][128] bf16 as two 64-wide K-major sub-tiles
+
+// NQ = number of Q buffers: 2 lets a CTA walk several heads of the same query tile back to back with the next
+// head's Q/K/V in flight (window layers: one K/V block per head, so per-CTA set-up and load latency would
+// otherwise dominate).
+template <int QTILES, int NKV, int NQ>
+struct AttnCfg {
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + NQ * QTILES * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + NKV * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + NKV * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + QTILES * P_BYTES;
+  static constexpr int BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = QTILES == 2 ? 512 : 256;
+  static constexpr int THREADS = 64 + 128 * QTILES;
+  __host__ __device__ static constexpr int S_COL(int t) { return t * 128; }
+  __host__ __device__ static constexpr int O_COL(int t) { return QTILES * 128 + t * 128; }
+};
+
+// ---- shared-memory operand descriptors (see ptx.cuh::umma_desc_k128 for the field layout)
+__device__ __forceinline__ uint64_t desc_common(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= layout << 61;
+  return d;
+}
+constexpr uint64_t SW128 = 2, SW32 = 6;
+// K-major, 32-byte rows (16 bf16), SWIZZLE_32B: 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t desc_k_sw32(uint32_t saddr) { return desc_common(saddr, 16, 256, SW32); }
+// MN-major B operand, rows = K index: 128-byte rows (64 bf16 of N), 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) { return desc_common(saddr, 1024, 1024, SW128); }
+// MN-major B operand, 32-byte rows (16 bf16 of N), 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t saddr) { return desc_common(saddr, 256, 256, SW32); }
+
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int QTILES, int NKV, int NQ>
+__global__ void __launch_bounds__(AttnCfg<QTILES, NKV, NQ>::THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
+               const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, __nv_bfloat16* __restrict__ out,
+               int m_rows, int heads, int heads_per_cta, float scale_log2) {
+  using L = AttnCfg<QTILES, NKV, NQ>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars;        // [NQ]
+  uint64_t* q_empty = q_full + NQ;
+  uint64_t* k_full = q_empty + NQ;
+  uint64_t* k_empty = k_full + NKV;
+  uint64_t* v_full = k_empty + NKV;
+  uint64_t* v_empty = v_full + NKV;
+  uint64_t* s_full = v_empty + NKV;  // [QTILES]
+  uint64_t* p_full = s_full + QTILES;
+  uint64_t* o_full = p_full + QTILES;
+  uint64_t* o_empty = o_full + QTILES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + QTILES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AttnTile tile = tiles[blockIdx.x];
+  const int head0 = blockIdx.y * heads_per_cta;
+  const int D = heads * HD;
+  const int nblk = tile.n_kv_blocks;
+  const int n_iter = heads_per_cta * nblk;  // flattened (head, kv block) iterations of this CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm64);
+    tma_prefetch_desc(&tm16);
+    for (int b = 0; b < NQ; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+    }
+    for (int b = 0; b < NKV; ++b) {
+      mbar_init(&k_full[b], 1);
+      mbar_init(&k_empty[b], 1);
+      mbar_init(&v_full[b], 1);
+      mbar_init(&v_empty[b], 1);
+    }
+    for (int t = 0; t < QTILES; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&o_full[t], 1);
+      mbar_init(&o_empty[t], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA loader =====================
+      int i = 0;
+      for (int hl = 0; hl < heads_per_cta; ++hl) {
+        const int head = head0 + hl;
+        const int qc = head * HD, kc = D + head * HD, vc = 2 * D + head * HD;
+        const int qb = hl % NQ;
+        uint8_t* qbuf = smem + L::OFF_Q + qb * QTILES * TILE_BYTES;
+        mbar_wait(&q_empty[qb], ((hl / NQ) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], QTILES * TILE_BYTES);
+#pragma unroll
+        for (int t = 0; t < QTILES; ++t) {
+          tma_load_2d(qbuf + t * TILE_BYTES, &tm64, &q_full[qb], qc, tile.q_row0 + t * QT);
+          tma_load_2d(qbuf + t * TILE_BYTES + T64_BYTES, &tm16, &q_full[qb], qc + 64, tile.q_row0 + t * QT);
+        }
+        for (int j = 0; j < nblk; ++j, ++i) {
+          const int b = i % NKV;
+          const uint32_t par = ((i / NKV) & 1) ^ 1;
+          const int row = tile.kv_row0 + j * KVB;
+          uint8_t* kb = smem + L::OFF_K + b * TILE_BYTES;
+          uint8_t* vb = smem + L::OFF_V + b * TILE_BYTES;
+          mbar_wait(&k_empty[b], par);
+          mbar_arrive_expect_tx(&k_full[b], TILE_BYTES);
+          tma_load_2d(kb, &tm64, &k_full[b], kc, row);
+          tma_load_2d(kb + T64_BYTES, &tm16, &k_full[b], kc + 64, row);
+          mbar_wait(&v_empty[b], par);
+          mbar_arrive_expect_tx(&v_full[b], TILE_BYTES);
+          tma_load_2d(vb, &tm64, &v_full[b], vc, row);
+          tma_load_2d(vb + T64_BYTES, &tm16, &v_full[b], vc + 64, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = idesc_bf16(QT, KVB, false);
+      constexpr uint32_t idesc_pv64 = idesc_bf16(QT, 64, true);
+      constexpr uint32_t idesc_pv16 = idesc_bf16(QT, 16, true);
+      auto issue_qk = [&](int t, int i) {  // S(t) is free: the caller has waited p_full(t, i-1)
+        const int b = i % NKV;
+        const int qb = (i / nblk) % NQ;
+        const uint32_t q64 = smem_u32(smem + L::OFF_Q + (qb * QTILES + t) * TILE_BYTES), q16 = q64 + T64_BYTES;
+        const uint32_t k64 = smem_u32(smem + L::OFF_K + b * TILE_BYTES), k16 = k64 + T64_BYTES;
+        const uint32_t ts = tmem_base + L::S_COL(t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(ts, umma_desc_k128(q64 + k * 32), umma_desc_k128(k64 + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+        umma_bf16_ss(ts, desc_k_sw32(q16), desc_k_sw32(k16), idesc_qk, 1u);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int i) {
+        const int b = i % NKV;
+        mbar_wait(&p_full[t], i & 1);         // softmax(t, i) has written P(t) and released S(t)
+        mbar_wait(&o_empty[t], (i & 1) ^ 1);  // accumulate(t, i-1) has drained O(t)
+        tc_fence_after();
+        const uint32_t p0 = smem_u32(smem + L::OFF_P + t * P_BYTES);
+        const uint32_t v64 = smem_u32(smem + L::OFF_V + b * TILE_BYTES), v16 = v64 + T64_BYTES;
+        const uint32_t to = tmem_base + L::O_COL(t);
+#pragma unroll
+        for (int k = 0; k < KVB / 16; ++k) {
+          const uint64_t pa = umma_desc_k128(p0 + (k >> 2) * T64_BYTES + (k & 3) * 32);
+          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv64, k != 0 ? 1u : 0u);
+          umma_bf16_ss(to + 64, pa, desc_mn_sw32(v16 + k * 512), idesc_pv16, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[t]);
+      };
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < QTILES; ++t) issue_qk(t, 0);
+      umma_commit(&k_empty[0]);
+      if (nblk == 1) umma_commit(&q_empty[0]);
+      for (int i = 0; i < n_iter; ++i) {
+        const int b = i % NKV;
+        mbar_wait(&v_full[b], (i / NKV) & 1);
+        const bool more = i + 1 < n_iter;
+        if (more) {
+          mbar_wait(&k_full[(i + 1) % NKV], ((i + 1) / NKV) & 1);
+          if ((i + 1) % nblk == 0) {  // first block of the next head: its Q must have landed
+            const int hl = (i + 1) / nblk;
+            mbar_wait(&q_full[hl % NQ], (hl / NQ) & 1);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < QTILES; ++t) {
+          issue_pv(t, i);
+          if (more) issue_qk(t, i + 1);
+        }
+        umma_commit(&v_empty[b]);
+        if (more) {
+          umma_commit(&k_empty[(i + 1) % NKV]);
+          if ((i + 1) % nblk == nblk - 1) umma_commit(&q_empty[((i + 1) / nblk) % NQ]);  // last Q K^T of that head
+        }
+      }
+    }
+  } else {
+    // ===================== softmax + output accumulation: one thread per query row =====================
+    const int t = (warp - 2) >> 2;   // query tile of this warp
+    const int quad = warp & 3;       // TMEM lane quadrant
+    const int r = quad * 32 + lane;  // row inside the tile == TMEM lane
+    const int row = tile.q_row0 + t * QT + r;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t ts = lane_base + L::S_COL(t);
+    const uint32_t to = lane_base + L::O_COL(t);
+    const uint32_t pbuf = smem_u32(smem + L::OFF_P + t * P_BYTES);
+    int2 bd = make_int2(0, 0);
+    if (row < m_rows) bd = bounds[row];
+    float o[HD];
+    float m_run, l_run, alpha_prev;
+
+    auto accumulate_block = [&](int i, float alpha) {
+      mbar_wait(&o_full[t], i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(to + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) o[c + i2] = o[c + i2] * alpha + __uint_as_float(v[i2]);
+      }
+      tc_fence_before();
+      mbar_arrive(&o_empty[t]);
+    };
+
+    for (int hl = 0; hl < heads_per_cta; ++hl) {
+    m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+#pragma unroll
+    for (int i2 = 0; i2 < HD; ++i2) o[i2] = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int it = hl * nblk + j;  // flattened iteration (barrier phases)
+      mbar_wait(&s_full[t], it & 1);
+      tc_fence_after();
+      // valid kv range of this row inside the block, in columns [0, 128)
+      const int kv0 = tile.kv_row0 + j * KVB;
+      const int lo = max(bd.x - kv0, 0), hi = min(bd.y - kv0, KVB);
+      // tcgen05.ld is warp-collective: skip / fast-path decisions are made per WARP (ballots), the
+      // per-row bounds only enter through the masked path.
+      // ---- pass 1: row maximum over the valid columns (64 columns per TMEM round trip)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KVB; c += 64) {
+        if (__all_sync(0xffffffffu, c + 64 <= lo || c >= hi)) continue;  // outside every row's segment
+        uint32_t v[64];
+        tmem_ld32(ts + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(ts + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        if (__all_sync(0xffffffffu, c >= lo && c + 64 <= hi)) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, (c + i >= lo && c + i < hi) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // nothing valid so far: p = 0, no NaN
+      const float alpha = ex2_approx(m_run - m_use);           // m_run = -inf -> 0
+      // ---- pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V); one 64-wide sub-tile per trip
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < KVB; c += 64) {
+        const uint32_t sub = pbuf + (c >> 6) * T64_BYTES;
+        if (__all_sync(0xffffffffu, c + 64 <= lo || c >= hi)) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) st_shared_v4(swz128(sub, r, q), 0u, 0u, 0u, 0u);
+          continue;
+        }
+        uint32_t v[64];
+        tmem_ld32(ts + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(ts + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        uint32_t pk[32];
+        if (__all_sync(0xffffffffu, c >= lo && c + 64 <= hi)) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const float p0 = ex2_approx(__uint_as_float(v[i]) * scale_log2 - m_use);
+            const float p1 = ex2_approx(__uint_as_float(v[i + 1]) * scale_log2 - m_use);
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            float p0 = ex2_approx(__uint_as_float(v[i]) * scale_log2 - m_use);
+            float p1 = ex2_approx(__uint_as_float(v[i + 1]) * scale_log2 - m_use);
+            p0 = (c + i >= lo && c + i < hi) ? p0 : 0.f;
+            p1 = (c + i + 1 >= lo && c + i + 1 < hi) ? p1 : 0.f;
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(swz128(sub, r, q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+      // the previous block's P V has long finished: fold it in while the tensor core works on this one
+      if (j >= 1) accumulate_block(it - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    accumulate_block(hl * nblk + nblk - 1, alpha_prev);
+
+    if (row < m_rows && bd.y > bd.x) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* op = out + static_cast<size_t>(row) * D + (head0 + hl) * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) {
+        *reinterpret_cast<uint4*>(op + c) =
+            make_uint4(pack_bf16x2(o[c] * inv, o[c + 1] * inv), pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv),
+                       pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
+      }
+    }
+    }  // heads of this CTA
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+template <int QTILES, int NKV, int NQ>
+int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, const int2* bd, __nv_bfloat16* o, int m_rows,
+                   int heads, int hpc, float scale_log2, cudaStream_t stream) {
+  using L = AttnCfg<QTILES, NKV, NQ>;
+  auto kern = attn_tc_kernel<QTILES, NKV, NQ>;
+  static bool attr = false;
+  if (!attr) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+    attr = true;
+  }
+  kern<<<dim3(n_tiles, heads / hpc), L::THREADS, L::BYTES, stream>>>(g.tm64, g.tm16, d_tiles, bd, o, m_rows, heads, hpc,
+                                                                     scale_log2);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// query tiles of `rows_per_tile` rows + per-row segment bounds from a cu_seqlens list
+void build_attn_tiles(const std::vector<int32_t>& cu, int m_rows, int rows_per_tile, std::vector<AttnTile>& tiles,
+                      std::vector<int32_t>& bounds) {
+  bounds.assign(static_cast<size_t>(m_rows) * 2, 0);
+  for (size_t s = 0; s + 1 < cu.size(); ++s)
+    for (int r = cu[s]; r < cu[s + 1] && r < m_rows; ++r) {
+      bounds[2 * r] = cu[s];
+      bounds[2 * r + 1] = cu[s + 1];
+    }
+  tiles.clear();
+  for (int q0 = 0; q0 < m_rows; q0 += rows_per_tile) {
+    int lo = INT_MAX, hi = 0;
+    for (int r = q0; r < q0 + rows_per_tile && r < m_rows; ++r) {
+      if (bounds[2 * r + 1] > bounds[2 * r]) {
+        lo = bounds[2 * r] < lo ? bounds[2 * r] : lo;
+        hi = bounds[2 * r + 1] > hi ? bounds[2 * r + 1] : hi;
+      }
+    }
+    if (hi <= lo) continue;  // no row of this tile belongs to a segment
+    tiles.push_back(AttnTile{q0, lo, (hi - lo + KVB - 1) / KVB, 0});
+  }
+}
+
+// rows_per_tile = 128 (window layers) or 256 (full layers), matching how `d_tiles` was built
+int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int n_tiles, int rows_per_tile, int max_blocks,
+                        const int32_t* d_bounds, int m_rows, int heads, cudaStream_t stream, AttnPrepared* cache) {
+  if (n_tiles <= 0) return 0;
+  AttnPrepared local;
+  AttnPrepared& g = cache ? *cache : local;
+  const int D = heads * HD;
+  if (!(g.valid && g.qkv == qkv && g.m_rows == m_rows && g.heads == heads)) {
+    int rc = make_tmap_2d(&g.tm64, qkv, m_rows, 3 * D, 3 * D, 2, 128, 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&g.tm16, qkv, m_rows, 3 * D, 3 * D, 2, 128, 16, 32);
+    if (rc) return rc;
+    g.qkv = qkv, g.m_rows = m_rows, g.heads = heads, g.valid = true;
+  }
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  const int2* bd = reinterpret_cast<const int2*>(d_bounds);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (rows_per_tile == 256) return launch_variant<2, 2, 1>(g, d_tiles, n_tiles, bd, o, m_rows, heads, 1, scale_log2, stream);
+  if (rows_per_tile != 128) return fail(B200VIT_EINVAL, "attention: rows_per_tile must be 128 or 256");
+  // window layers: several heads per CTA (next head's operands prefetched), as many as keep ~one CTA per SM
+  int hpc = 1;
+  const int sms = device_sm_count();
+  for (int c = 8; c >= 2; c >>= 1)
+    if (heads % c == 0 && n_tiles * (heads / c) >= (sms * 3) / 4) {
+      hpc = c;
+      break;
+    }
+  (void)max_blocks;
+  return launch_variant<1, 2, 2>(g, d_tiles, n_tiles, bd, o, m_rows, heads, hpc, scale_log2, stream);
+}
+
+}  // namespace b200

@@ -79,10 +79,6 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float4 bias4(const float* bias, int col, int n) {
   return (col + 4 <= n) ? ldg4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
-// 16-byte chunk j of row `lane` inside a [32 rows x 128 B] SWIZZLE_128B box at `base` (1024-aligned)
-__device__ __forceinline__ uint32_t swz128(uint32_t base, int lane, int j) {
-  return base + lane * 128 + ((j ^ (lane & 7)) << 4);
-}
 
 // ------------------------------------------------------------------ epilogues
 // Each epilogue thread owns one accumulator row (TMEM lane) and CW consecutive columns.
@@ -529,10 +525,10 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     rc = make_tmap_bf16(&g.tb, a.d_b, a.n, a.k, C::BN_LOAD);
     if (rc) return rc;
     g.to = g.ta;
-    if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, false);
-    else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, true);
-    else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, true);
-    else if (EPI == B200VIT_EPI_BIAS_GELU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 64, true);
+    if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, 0);
+    else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, 128);
+    else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, 128);
+    else if (EPI == B200VIT_EPI_BIAS_GELU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 64, 128);
     if (rc) return rc;
     const int num_tiles = ((a.m + MT - 1) / MT) * ((a.n + BN - 1) / BN);
     const int sms = device_sm_count();

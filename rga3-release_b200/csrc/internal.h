@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/b200vit.h"
 
@@ -27,9 +28,9 @@ int check_arch();  // 0 if the current device is sm_100, else B200VIT_EARCH
 // out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
 // General 2-D row-major map: elem_bytes 2 (bf16) or 4 (fp32), row pitch `pitch_elems`, box = [box_rows, box_cols],
-// swizzle128 = SWIZZLE_128B (box_cols * elem_bytes must be 128) or no swizzle.
+// swizzle_bytes = 0 (none), 32 or 128 (box_cols * elem_bytes must equal the swizzle width).
 int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int elem_bytes,
-                 int box_rows, int box_cols, bool swizzle128);
+                 int box_rows, int box_cols, int swizzle_bytes);
 
 // kernels (all enqueue on `stream`, no host sync)
 // Host-side memo of one GEMM call site: tensor maps and launch geometry are rebuilt only when the
@@ -48,6 +49,21 @@ struct AttnWork {  // one CTA of the attention kernel: <= 64 query rows of one s
   int32_t q_start, q_len, kv_start, kv_len;
 };
 int launch_attention(const void* qkv, void* out, const AttnWork* d_work, int n_work, int heads, cudaStream_t stream);
+
+// tcgen05 attention (attention_tc.cu): one CTA = 128 query rows of one head
+struct AttnTile {
+  int32_t q_row0, kv_row0, n_kv_blocks, pad;
+};
+struct AttnPrepared {  // host memo of the two tensor maps over the qkv buffer
+  bool valid = false;
+  const void* qkv = nullptr;
+  int m_rows = 0, heads = 0;
+  CUtensorMap tm64, tm16;
+};
+void build_attn_tiles(const std::vector<int32_t>& cu, int m_rows, int rows_per_tile, std::vector<AttnTile>& tiles,
+                      std::vector<int32_t>& bounds);
+int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int n_tiles, int rows_per_tile, int max_blocks,
+                        const int32_t* d_bounds, int m_rows, int heads, cudaStream_t stream, AttnPrepared* cache);
 
 struct OverlayDev;  // device-side overlay description (overlay.cu)
 int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov, int patch, int tps, int merge,

@@ -99,6 +99,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// shared address of 16-byte chunk j of row `row` inside a [rows x 128 B] SWIZZLE_128B tile at `base` (1024-aligned)
+__device__ __forceinline__ uint32_t swz128(uint32_t base, int row, int j) {
+  return base + row * 128 + ((j ^ (row & 7)) << 4);
+}
+
 // ---------------------------------------------------------------- clusters / CTA pairs
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
