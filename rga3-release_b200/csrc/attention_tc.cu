@@ -37,19 +37,24 @@ constexpr int T16_BYTES = 128 * 32;   // [128 rows][16 cols] bf16
 constexpr int TILE_BYTES = T64_BYTES + T16_BYTES;
 constexpr int P_BYTES = 2 * T64_BYTES;  // [128][128] bf16 as two 64-wide K-major sub-tiles
 
-// NQ = number of Q buffers: 2 lets a CTA walk several heads of the same query tile back to back with the next
-// head's Q/K/V in flight (window layers: one K/V block per head, so per-CTA set-up and load latency would
-// otherwise dominate).
-template <int QTILES, int NKV, int NQ>
+// SHARED_KV = true  (full layers): the QTILES query tiles are consecutive 128-row tiles of ONE head and share
+//                     each K/V block (NKV-deep ring); the CTA may walk several heads (NQ Q buffers).
+// SHARED_KV = false (window layers): the QTILES "tiles" are the SAME 128 rows of DIFFERENT heads -- two fully
+//                     independent (Q, K, V) streams, each with its own softmax warpgroup, interleaved on the
+//                     one MMA issuer so one stream's softmax hides the other's tensor-core and load latency.
+template <int QTILES, int NKV, int NQ, bool SHARED_KV>
 struct AttnCfg {
+  static constexpr int NQBUF = SHARED_KV ? NQ * QTILES : QTILES;
+  static constexpr int NKBUF = SHARED_KV ? NKV : QTILES;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + NQ * QTILES * TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + NKV * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + NKV * TILE_BYTES;
+  static constexpr int OFF_K = OFF_Q + NQBUF * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + NKBUF * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + NKBUF * TILE_BYTES;
   static constexpr int OFF_BAR = OFF_P + QTILES * P_BYTES;
   static constexpr int BYTES = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = QTILES == 2 ? 512 : 256;
   static constexpr int THREADS = 64 + 128 * QTILES;
+  static constexpr int NQBAR = SHARED_KV ? NQ : QTILES;
   __host__ __device__ static constexpr int S_COL(int t) { return t * 128; }
   __host__ __device__ static constexpr int O_COL(int t) { return QTILES * 128 + t * 128; }
 };
@@ -83,22 +88,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int QTILES, int NKV, int NQ>
-__global__ void __launch_bounds__(AttnCfg<QTILES, NKV, NQ>::THREADS, 1)
+template <int QTILES, int NKV, int NQ, bool SHARED_KV>
+__global__ void __launch_bounds__(AttnCfg<QTILES, NKV, NQ, SHARED_KV>::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, __nv_bfloat16* __restrict__ out,
                int m_rows, int heads, int heads_per_cta, float scale_log2) {
-  using L = AttnCfg<QTILES, NKV, NQ>;
+  using L = AttnCfg<QTILES, NKV, NQ, SHARED_KV>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* q_full = bars;        // [NQ]
-  uint64_t* q_empty = q_full + NQ;
-  uint64_t* k_full = q_empty + NQ;
-  uint64_t* k_empty = k_full + NKV;
-  uint64_t* v_full = k_empty + NKV;
-  uint64_t* v_empty = v_full + NKV;
-  uint64_t* s_full = v_empty + NKV;  // [QTILES]
+  uint64_t* q_full = bars;  // [NQBAR]
+  uint64_t* q_empty = q_full + L::NQBAR;
+  uint64_t* k_full = q_empty + L::NQBAR;  // [NKBUF]
+  uint64_t* k_empty = k_full + L::NKBUF;
+  uint64_t* v_full = k_empty + L::NKBUF;
+  uint64_t* v_empty = v_full + L::NKBUF;
+  uint64_t* s_full = v_empty + L::NKBUF;  // [QTILES]
   uint64_t* p_full = s_full + QTILES;
   uint64_t* o_full = p_full + QTILES;
   uint64_t* o_empty = o_full + QTILES;
@@ -109,16 +114,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   const int head0 = blockIdx.y * heads_per_cta;
   const int D = heads * HD;
   const int nblk = tile.n_kv_blocks;
-  const int n_iter = heads_per_cta * nblk;  // flattened (head, kv block) iterations of this CTA
+  // head iterations per stream and flattened (head, kv block) iterations
+  const int n_hl = SHARED_KV ? heads_per_cta : heads_per_cta / QTILES;
+  const int n_iter = n_hl * nblk;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm64);
     tma_prefetch_desc(&tm16);
-    for (int b = 0; b < NQ; ++b) {
+    for (int b = 0; b < L::NQBAR; ++b) {
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
     }
-    for (int b = 0; b < NKV; ++b) {
+    for (int b = 0; b < L::NKBUF; ++b) {
       mbar_init(&k_full[b], 1);
       mbar_init(&k_empty[b], 1);
       mbar_init(&v_full[b], 1);
@@ -144,34 +151,53 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA loader =====================
-      int i = 0;
-      for (int hl = 0; hl < heads_per_cta; ++hl) {
-        const int head = head0 + hl;
-        const int qc = head * HD, kc = D + head * HD, vc = 2 * D + head * HD;
-        const int qb = hl % NQ;
-        uint8_t* qbuf = smem + L::OFF_Q + qb * QTILES * TILE_BYTES;
-        mbar_wait(&q_empty[qb], ((hl / NQ) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[qb], QTILES * TILE_BYTES);
+      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+        tma_load_2d(dst, &tm64, bar, col, row);
+        tma_load_2d(dst + T64_BYTES, &tm16, bar, col + 64, row);
+      };
+      if constexpr (SHARED_KV) {
+        int i = 0;
+        for (int hl = 0; hl < n_hl; ++hl) {
+          const int head = head0 + hl;
+          const int qb = hl % NQ;
+          mbar_wait(&q_empty[qb], ((hl / NQ) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qb], QTILES * TILE_BYTES);
 #pragma unroll
-        for (int t = 0; t < QTILES; ++t) {
-          tma_load_2d(qbuf + t * TILE_BYTES, &tm64, &q_full[qb], qc, tile.q_row0 + t * QT);
-          tma_load_2d(qbuf + t * TILE_BYTES + T64_BYTES, &tm16, &q_full[qb], qc + 64, tile.q_row0 + t * QT);
+          for (int t = 0; t < QTILES; ++t)
+            load_tile(smem + L::OFF_Q + (qb * QTILES + t) * TILE_BYTES, &q_full[qb], head * HD, tile.q_row0 + t * QT);
+          for (int j = 0; j < nblk; ++j, ++i) {
+            const int b = i % NKV;
+            const uint32_t par = ((i / NKV) & 1) ^ 1;
+            const int row = tile.kv_row0 + j * KVB;
+            mbar_wait(&k_empty[b], par);
+            mbar_arrive_expect_tx(&k_full[b], TILE_BYTES);
+            load_tile(smem + L::OFF_K + b * TILE_BYTES, &k_full[b], D + head * HD, row);
+            mbar_wait(&v_empty[b], par);
+            mbar_arrive_expect_tx(&v_full[b], TILE_BYTES);
+            load_tile(smem + L::OFF_V + b * TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
+          }
         }
-        for (int j = 0; j < nblk; ++j, ++i) {
-          const int b = i % NKV;
-          const uint32_t par = ((i / NKV) & 1) ^ 1;
-          const int row = tile.kv_row0 + j * KVB;
-          uint8_t* kb = smem + L::OFF_K + b * TILE_BYTES;
-          uint8_t* vb = smem + L::OFF_V + b * TILE_BYTES;
-          mbar_wait(&k_empty[b], par);
-          mbar_arrive_expect_tx(&k_full[b], TILE_BYTES);
-          tma_load_2d(kb, &tm64, &k_full[b], kc, row);
-          tma_load_2d(kb + T64_BYTES, &tm16, &k_full[b], kc + 64, row);
-          mbar_wait(&v_empty[b], par);
-          mbar_arrive_expect_tx(&v_full[b], TILE_BYTES);
-          tma_load_2d(vb, &tm64, &v_full[b], vc, row);
-          tma_load_2d(vb + T64_BYTES, &tm16, &v_full[b], vc + 64, row);
-        }
+      } else {
+        for (int hl = 0; hl < n_hl; ++hl)
+          for (int j = 0; j < nblk; ++j)
+#pragma unroll
+            for (int t = 0; t < QTILES; ++t) {
+              const int head = head0 + hl * QTILES + t;
+              const int it = hl * nblk + j;
+              const uint32_t par = (it & 1) ^ 1;
+              const int row = tile.kv_row0 + j * KVB;
+              if (j == 0) {
+                mbar_wait(&q_empty[t], (hl & 1) ^ 1);
+                mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+                load_tile(smem + L::OFF_Q + t * TILE_BYTES, &q_full[t], head * HD, tile.q_row0);
+              }
+              mbar_wait(&k_empty[t], par);
+              mbar_arrive_expect_tx(&k_full[t], TILE_BYTES);
+              load_tile(smem + L::OFF_K + t * TILE_BYTES, &k_full[t], D + head * HD, row);
+              mbar_wait(&v_empty[t], par);
+              mbar_arrive_expect_tx(&v_full[t], TILE_BYTES);
+              load_tile(smem + L::OFF_V + t * TILE_BYTES, &v_full[t], 2 * D + head * HD, row);
+            }
       }
     }
   } else if (warp == 1) {
@@ -180,11 +206,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
       constexpr uint32_t idesc_qk = idesc_bf16(QT, KVB, false);
       constexpr uint32_t idesc_pv64 = idesc_bf16(QT, 64, true);
       constexpr uint32_t idesc_pv16 = idesc_bf16(QT, 16, true);
+      auto kv_stage = [&](int t, int i) { return SHARED_KV ? (i % NKV) : t; };
+      auto q_slot = [&](int t, int i) { return SHARED_KV ? (((i / nblk) % NQ) * QTILES + t) : t; };
       auto issue_qk = [&](int t, int i) {  // S(t) is free: the caller has waited p_full(t, i-1)
-        const int b = i % NKV;
-        const int qb = (i / nblk) % NQ;
-        const uint32_t q64 = smem_u32(smem + L::OFF_Q + (qb * QTILES + t) * TILE_BYTES), q16 = q64 + T64_BYTES;
-        const uint32_t k64 = smem_u32(smem + L::OFF_K + b * TILE_BYTES), k16 = k64 + T64_BYTES;
+        const uint32_t q64 = smem_u32(smem + L::OFF_Q + q_slot(t, i) * TILE_BYTES), q16 = q64 + T64_BYTES;
+        const uint32_t k64 = smem_u32(smem + L::OFF_K + kv_stage(t, i) * TILE_BYTES), k16 = k64 + T64_BYTES;
         const uint32_t ts = tmem_base + L::S_COL(t);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -193,12 +219,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         umma_commit(&s_full[t]);
       };
       auto issue_pv = [&](int t, int i) {
-        const int b = i % NKV;
         mbar_wait(&p_full[t], i & 1);         // softmax(t, i) has written P(t) and released S(t)
         mbar_wait(&o_empty[t], (i & 1) ^ 1);  // accumulate(t, i-1) has drained O(t)
         tc_fence_after();
         const uint32_t p0 = smem_u32(smem + L::OFF_P + t * P_BYTES);
-        const uint32_t v64 = smem_u32(smem + L::OFF_V + b * TILE_BYTES), v16 = v64 + T64_BYTES;
+        const uint32_t v64 = smem_u32(smem + L::OFF_V + kv_stage(t, i) * TILE_BYTES), v16 = v64 + T64_BYTES;
         const uint32_t to = tmem_base + L::O_COL(t);
 #pragma unroll
         for (int k = 0; k < KVB / 16; ++k) {
@@ -208,33 +233,62 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         }
         umma_commit(&o_full[t]);
       };
-      mbar_wait(&q_full[0], 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
+      if constexpr (SHARED_KV) {
+        mbar_wait(&q_full[0], 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
 #pragma unroll
-      for (int t = 0; t < QTILES; ++t) issue_qk(t, 0);
-      umma_commit(&k_empty[0]);
-      if (nblk == 1) umma_commit(&q_empty[0]);
-      for (int i = 0; i < n_iter; ++i) {
-        const int b = i % NKV;
-        mbar_wait(&v_full[b], (i / NKV) & 1);
-        const bool more = i + 1 < n_iter;
-        if (more) {
-          mbar_wait(&k_full[(i + 1) % NKV], ((i + 1) / NKV) & 1);
-          if ((i + 1) % nblk == 0) {  // first block of the next head: its Q must have landed
-            const int hl = (i + 1) / nblk;
-            mbar_wait(&q_full[hl % NQ], (hl / NQ) & 1);
+        for (int t = 0; t < QTILES; ++t) issue_qk(t, 0);
+        umma_commit(&k_empty[0]);
+        if (nblk == 1) umma_commit(&q_empty[0]);
+        for (int i = 0; i < n_iter; ++i) {
+          const int b = i % NKV;
+          mbar_wait(&v_full[b], (i / NKV) & 1);
+          const bool more = i + 1 < n_iter;
+          if (more) {
+            mbar_wait(&k_full[(i + 1) % NKV], ((i + 1) / NKV) & 1);
+            if ((i + 1) % nblk == 0) {  // first block of the next head: its Q must have landed
+              const int hl = (i + 1) / nblk;
+              mbar_wait(&q_full[hl % NQ], (hl / NQ) & 1);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < QTILES; ++t) {
+            issue_pv(t, i);
+            if (more) issue_qk(t, i + 1);
+          }
+          umma_commit(&v_empty[b]);
+          if (more) {
+            umma_commit(&k_empty[(i + 1) % NKV]);
+            if ((i + 1) % nblk == nblk - 1) umma_commit(&q_empty[((i + 1) / nblk) % NQ]);  // last Q K^T of that head
           }
         }
+      } else {
 #pragma unroll
         for (int t = 0; t < QTILES; ++t) {
-          issue_pv(t, i);
-          if (more) issue_qk(t, i + 1);
+          mbar_wait(&q_full[t], 0);
+          mbar_wait(&k_full[t], 0);
+          tc_fence_after();
+          issue_qk(t, 0);
+          umma_commit(&k_empty[t]);
+          if (nblk == 1) umma_commit(&q_empty[t]);
         }
-        umma_commit(&v_empty[b]);
-        if (more) {
-          umma_commit(&k_empty[(i + 1) % NKV]);
-          if ((i + 1) % nblk == nblk - 1) umma_commit(&q_empty[((i + 1) / nblk) % NQ]);  // last Q K^T of that head
+        for (int i = 0; i < n_iter; ++i) {
+          const bool more = i + 1 < n_iter;
+#pragma unroll
+          for (int t = 0; t < QTILES; ++t) {
+            mbar_wait(&v_full[t], i & 1);
+            issue_pv(t, i);
+            umma_commit(&v_empty[t]);
+            if (more) {
+              mbar_wait(&k_full[t], (i + 1) & 1);
+              if ((i + 1) % nblk == 0) mbar_wait(&q_full[t], ((i + 1) / nblk) & 1);
+              tc_fence_after();
+              issue_qk(t, i + 1);
+              umma_commit(&k_empty[t]);
+              if ((i + 1) % nblk == nblk - 1) umma_commit(&q_empty[t]);
+            }
+          }
         }
       }
     }
@@ -243,7 +297,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
     const int t = (warp - 2) >> 2;   // query tile of this warp
     const int quad = warp & 3;       // TMEM lane quadrant
     const int r = quad * 32 + lane;  // row inside the tile == TMEM lane
-    const int row = tile.q_row0 + t * QT + r;
+    const int row = tile.q_row0 + (SHARED_KV ? t * QT : 0) + r;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t ts = lane_base + L::S_COL(t);
     const uint32_t to = lane_base + L::O_COL(t);
@@ -268,7 +322,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
       mbar_arrive(&o_empty[t]);
     };
 
-    for (int hl = 0; hl < heads_per_cta; ++hl) {
+    for (int hl = 0; hl < n_hl; ++hl) {
     m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
 #pragma unroll
     for (int i2 = 0; i2 < HD; ++i2) o[i2] = 0.f;
@@ -352,7 +406,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 
     if (row < m_rows && bd.y > bd.x) {
       const float inv = 1.f / l_run;
-      __nv_bfloat16* op = out + static_cast<size_t>(row) * D + (head0 + hl) * HD;
+      const int head = SHARED_KV ? head0 + hl : head0 + hl * QTILES + t;
+      __nv_bfloat16* op = out + static_cast<size_t>(row) * D + head * HD;
 #pragma unroll
       for (int c = 0; c < HD; c += 8) {
         *reinterpret_cast<uint4*>(op + c) =
@@ -371,11 +426,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   }
 }
 
-template <int QTILES, int NKV, int NQ>
+template <int QTILES, int NKV, int NQ, bool SHARED_KV>
 int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, const int2* bd, __nv_bfloat16* o, int m_rows,
                    int heads, int hpc, float scale_log2, cudaStream_t stream) {
-  using L = AttnCfg<QTILES, NKV, NQ>;
-  auto kern = attn_tc_kernel<QTILES, NKV, NQ>;
+  using L = AttnCfg<QTILES, NKV, NQ, SHARED_KV>;
+  auto kern = attn_tc_kernel<QTILES, NKV, NQ, SHARED_KV>;
   static bool attr = false;
   if (!attr) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
@@ -429,18 +484,21 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int2* bd = reinterpret_cast<const int2*>(d_bounds);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (rows_per_tile == 256) return launch_variant<2, 2, 1>(g, d_tiles, n_tiles, bd, o, m_rows, heads, 1, scale_log2, stream);
+  if (rows_per_tile == 256)
+    return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, o, m_rows, heads, 1, scale_log2, stream);
   if (rows_per_tile != 128) return fail(B200VIT_EINVAL, "attention: rows_per_tile must be 128 or 256");
-  // window layers: several heads per CTA (next head's operands prefetched), as many as keep ~one CTA per SM
-  int hpc = 1;
+  (void)max_blocks;
+  if (heads % 2 != 0)  // odd head count: single stream, K/V double-buffered
+    return launch_variant<1, 2, 2, true>(g, d_tiles, n_tiles, bd, o, m_rows, heads, 1, scale_log2, stream);
+  // window layers: two heads in flight per CTA; walk as many head pairs per CTA as keep ~one CTA per SM
+  int hpc = 2;
   const int sms = device_sm_count();
-  for (int c = 8; c >= 2; c >>= 1)
+  for (int c = 8; c >= 4; c >>= 1)
     if (heads % c == 0 && n_tiles * (heads / c) >= (sms * 3) / 4) {
       hpc = c;
       break;
     }
-  (void)max_blocks;
-  return launch_variant<1, 2, 2>(g, d_tiles, n_tiles, bd, o, m_rows, heads, hpc, scale_log2, stream);
+  return launch_variant<2, 1, 1, false>(g, d_tiles, n_tiles, bd, o, m_rows, heads, hpc, scale_log2, stream);
 }
 
 }  // namespace b200
