@@ -35,6 +35,8 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
 __global__ void __launch_bounds__(128)
 attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                    const AttnWork* __restrict__ work, int heads, float scale_log2) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sK = sQ + TILE_ELEMS;       // [2][64][LDS]

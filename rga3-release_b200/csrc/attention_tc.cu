@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -94,6 +95,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
                const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, __nv_bfloat16* __restrict__ out,
                int m_rows, int heads, int heads_per_cta, float scale_log2) {
   using L = AttnCfg<QTILES, NKV, NQ, SHARED_KV>;
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -147,6 +149,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -436,9 +439,8 @@ int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, 
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
     attr = true;
   }
-  kern<<<dim3(n_tiles, heads / hpc), L::THREADS, L::BYTES, stream>>>(g.tm64, g.tm16, d_tiles, bd, o, m_rows, heads, hpc,
-                                                                     scale_log2);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_kernel(kern, dim3(n_tiles, heads / hpc), dim3(L::THREADS), L::BYTES, stream, 1, g.tm64, g.tm16, d_tiles, bd,
+                             o, m_rows, heads, hpc, scale_log2));
   return 0;
 }
 

@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -17,6 +18,8 @@ constexpr int RMS_MAX_V4 = 16;  // float4 per lane held in registers: rows up to
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows,
                int dim, float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= rows) return;
@@ -66,6 +69,8 @@ __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v)
 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i0 + 8 <= n) {
     float f[8];
@@ -94,8 +99,8 @@ int launch_rmsnorm(const float* x, const float* w, void* out_bf16, int rows, int
     return fail(B200VIT_EALIGN, "rmsnorm: pointers must be 16-byte aligned");
   const int warps_per_block = 8;
   const int grid = (rows + warps_per_block - 1) / warps_per_block;
-  rmsnorm_kernel<<<grid, warps_per_block * 32, 0, stream>>>(x, w, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, dim, eps);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_kernel(rmsnorm_kernel, dim3(grid), dim3(warps_per_block * 32), 0, stream, 1, x, w,
+                             reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, dim, eps));
   return 0;
 }
 
@@ -106,9 +111,11 @@ int launch_cast_bf16(const void* in, int in_dtype, void* out, int64_t n, cudaStr
   const int64_t threads = (n + 7) / 8;
   const int grid = static_cast<int>((threads + 255) / 256);
   if (in_dtype == 0)
-    cast_bf16_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(in), reinterpret_cast<__nv_bfloat16*>(out), n);
+    B200_CUDA_OK(launch_kernel(cast_bf16_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const float*>(in),
+                               reinterpret_cast<__nv_bfloat16*>(out), n));
   else if (in_dtype == 1)
-    cast_bf16_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__nv_bfloat16*>(out), n);
+    B200_CUDA_OK(launch_kernel(cast_bf16_kernel<__half>, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __half*>(in),
+                               reinterpret_cast<__nv_bfloat16*>(out), n));
   else if (in_dtype == 2)
     B200_CUDA_OK(cudaMemcpyAsync(out, in, n * 2, cudaMemcpyDeviceToDevice, stream));
   else

@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -349,6 +350,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
@@ -388,6 +390,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -556,19 +559,7 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(g.grid);
-  cfg.blockDim = dim3(128 + 128 * EG);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.ta, g.tb, g.to, p));
+  B200_CUDA_OK(launch_kernel(kern, dim3(g.grid), dim3(128 + 128 * EG), C::SMEM_BYTES, stream, PAIR ? 2 : 1, g.ta, g.tb, g.to, p));
   return 0;
 }
 

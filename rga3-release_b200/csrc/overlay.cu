@@ -17,6 +17,7 @@
 #include <cstring>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -108,9 +109,11 @@ template <bool HAS_OVERLAY>
 __global__ void __launch_bounds__(256)
 overlay_patchify_kernel(const __grid_constant__ PatchParams p, const __grid_constant__ OverlayParams ov,
                         __nv_bfloat16* __restrict__ out) {
+  griddep_launch_dependents();
   __shared__ uint16_t lut[3 * 256];
   for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = c_norm_lut[i];
   __syncthreads();
+  griddep_wait();  // the output buffer may still be read by the previous forward's patch-embed GEMM
   const int chunks = p.cols >> 3;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= p.rows * chunks) return;
@@ -300,9 +303,9 @@ int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov,
       const int grid = static_cast<int>((threads + 255) / 256);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_bf16) + p.row_base * cols;
       if (ov != nullptr && ov->h_ops != nullptr)
-        overlay_patchify_kernel<true><<<grid, 256, 0, stream>>>(p, o, dst);
+        B200_CUDA_OK(launch_kernel(overlay_patchify_kernel<true>, dim3(grid), dim3(256), 0, stream, 1, p, o, dst));
       else
-        overlay_patchify_kernel<false><<<grid, 256, 0, stream>>>(p, o, dst);
+        B200_CUDA_OK(launch_kernel(overlay_patchify_kernel<false>, dim3(grid), dim3(256), 0, stream, 1, p, o, dst));
     }
     if (out_u8) {
       const int64_t npx = static_cast<int64_t>(nf) * fr.h * fr.w;
