@@ -197,6 +197,59 @@ bool legacy_attention() {  // B200VIT_ATTN=legacy selects the mma.sync kernel (A
   return v == 1;
 }
 
+// Keep the fp32 residual stream resident in L2 across the ~250 MB of other traffic each block generates:
+// x is read by both RMSNorms and read-modify-written by both residual GEMMs of every block (SURVEY.md 8d:
+// 252 MB of HBM traffic per block otherwise).  Implemented as a persisting access-policy window on the
+// caller's stream for the duration of the forward.  B200VIT_L2_PERSIST=0 disables it.
+struct L2Persist {
+  cudaStream_t stream;
+  bool active = false;
+  L2Persist(cudaStream_t st, void* base, size_t bytes) : stream(st) {
+    static int enabled = -1;
+    static size_t max_persist = 0, max_window = 0;
+    if (enabled < 0) {
+      const char* e = getenv("B200VIT_L2_PERSIST");
+      enabled = (e == nullptr || e[0] != '0') ? 1 : 0;
+      int dev = 0, v = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      max_persist = static_cast<size_t>(v);
+      cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      max_window = static_cast<size_t>(v);
+      if (!(enabled && max_persist > 0)) enabled = 0;
+      cudaGetLastError();
+    }
+    if (!enabled || bytes == 0) return;
+    static size_t set_aside = 0;  // carve out only what the residual stream needs: the rest stays normal L2
+    const size_t want = bytes < max_persist ? bytes : max_persist;
+    if (want != set_aside) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+      }
+      set_aside = want;
+    }
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    const size_t win = bytes < max_window ? bytes : max_window;
+    attr.accessPolicyWindow.base_ptr = base;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win <= max_persist ? 1.0f : static_cast<float>(max_persist) / static_cast<float>(win);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    active = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+    cudaGetLastError();
+  }
+  ~L2Persist() {
+    if (!active) return;
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.num_bytes = 0;  // disables the window for later work on this stream
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+  }
+};
+
 bool is_fullatt(const b200vit_cfg& c, int layer) {
   for (int i = 0; i < c.n_fullatt; ++i)
     if (c.fullatt[i] == layer) return true;
@@ -343,6 +396,7 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
   int site = 0;
   Prof prof{p, stream};
   p->ev_used = 0;
+  L2Persist keep_x(stream, x, static_cast<size_t>(M) * D * 4);
   const void* a0 = d_pixel_values;
   if (frames) {
     if (p->grid.size() != 3) return fail(B200VIT_EINVAL, "forward: the frames entry takes a single-clip plan");

@@ -5,6 +5,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "internal.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -12,51 +14,58 @@
 namespace b200 {
 namespace {
 
-constexpr int RMS_MAX_V4 = 16;  // float4 per lane held in registers: rows up to 2048 floats
-
 // HF modeling_qwen2_5_vl.py:66-71: w * (x * rsqrt(mean(x^2) + eps)) with fp32 statistics.
-__global__ void __launch_bounds__(256)
+// NV = float4 per lane (dim = 128 * NV), compile-time so all loads of a row are issued back to back;
+// NV = 0 is the generic two-pass fallback.  Rows are distributed warp-by-warp over a grid sized to the
+// machine (grid-stride), so the tail is one row, not one block.
+template <int NV>
+__global__ void __launch_bounds__(128)
 rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows,
                int dim, float eps) {
   griddep_launch_dependents();
-  griddep_wait();
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp_global >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp_global) * dim);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
   const float4* wr = reinterpret_cast<const float4*>(w);
-  const int nv = dim >> 2;
-  float4 v[RMS_MAX_V4];
-  float ss = 0.f;
+  const float inv_dim = 1.0f / static_cast<float>(dim);
+  float4 g[NV > 0 ? NV : 1];
+  if constexpr (NV > 0) {
 #pragma unroll
-  for (int i = 0; i < RMS_MAX_V4; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      v[i] = xr[idx];
-      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    for (int i = 0; i < NV; ++i) g[i] = __ldg(wr + lane + i * 32);  // norm weights do not depend on the previous kernel
+  }
+  griddep_wait();
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * dim);
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * dim);
+    if constexpr (NV > 0) {
+      float4 v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = xr[lane + i * 32];
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss * inv_dim + eps);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        orow[lane + i * 32] = make_uint2(pack_bf16x2(v[i].x * rstd * g[i].x, v[i].y * rstd * g[i].y),
+                                         pack_bf16x2(v[i].z * rstd * g[i].z, v[i].w * rstd * g[i].w));
+    } else {
+      const int nv = dim >> 2;
+      float ss = 0.f;
+      for (int idx = lane; idx < nv; idx += 32) {
+        const float4 t = xr[idx];
+        ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss * inv_dim + eps);
+      for (int idx = lane; idx < nv; idx += 32) {
+        const float4 t = xr[idx];
+        const float4 gg = __ldg(wr + idx);
+        orow[idx] = make_uint2(pack_bf16x2(t.x * rstd * gg.x, t.y * rstd * gg.y), pack_bf16x2(t.z * rstd * gg.z, t.w * rstd * gg.w));
+      }
     }
-  }
-  for (int idx = lane + RMS_MAX_V4 * 32; idx < nv; idx += 32) {  // rows longer than the register cache
-    float4 t = xr[idx];
-    ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / static_cast<float>(dim) + eps);
-  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(warp_global) * dim);
-#pragma unroll
-  for (int i = 0; i < RMS_MAX_V4; ++i) {
-    const int idx = lane + i * 32;
-    if (idx < nv) {
-      const float4 g = __ldg(wr + idx);
-      orow[idx] = make_uint2(pack_bf16x2(v[i].x * rstd * g.x, v[i].y * rstd * g.y),
-                             pack_bf16x2(v[i].z * rstd * g.z, v[i].w * rstd * g.w));
-    }
-  }
-  for (int idx = lane + RMS_MAX_V4 * 32; idx < nv; idx += 32) {
-    const float4 t = xr[idx];
-    const float4 g = __ldg(wr + idx);
-    orow[idx] = make_uint2(pack_bf16x2(t.x * rstd * g.x, t.y * rstd * g.y), pack_bf16x2(t.z * rstd * g.z, t.w * rstd * g.w));
   }
 }
 
@@ -97,10 +106,18 @@ int launch_rmsnorm(const float* x, const float* w, void* out_bf16, int rows, int
   if (dim % 4) return fail(B200VIT_EINVAL, "rmsnorm: dim must be a multiple of 4");
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out_bf16)) & 15)
     return fail(B200VIT_EALIGN, "rmsnorm: pointers must be 16-byte aligned");
-  const int warps_per_block = 8;
-  const int grid = (rows + warps_per_block - 1) / warps_per_block;
-  B200_CUDA_OK(launch_kernel(rmsnorm_kernel, dim3(grid), dim3(warps_per_block * 32), 0, stream, 1, x, w,
-                             reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, dim, eps));
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    const char* e = getenv("B200VIT_RMS_BPS");
+    blocks_per_sm = e ? atoi(e) : 8;
+  }
+  int grid = device_sm_count() * blocks_per_sm;  // 4 warps per block
+  if (grid > (rows + 3) / 4) grid = (rows + 3) / 4;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (dim == 1280)
+    B200_CUDA_OK(launch_kernel(rmsnorm_kernel<10>, dim3(grid), dim3(128), 0, stream, 1, x, w, o, rows, dim, eps));
+  else
+    B200_CUDA_OK(launch_kernel(rmsnorm_kernel<0>, dim3(grid), dim3(128), 0, stream, 1, x, w, o, rows, dim, eps));
   return 0;
 }
 
