@@ -44,10 +44,14 @@ struct GemmParams {
   int stream_k;  // 1: stream-K decomposition (BIAS_RESIDUAL only)
 };
 
+#ifndef B200_RESID_BUFS
+#define B200_RESID_BUFS 1
+#endif
+constexpr int RESID_BUFS = B200_RESID_BUFS;  // staging buffers per warp of the reduce-add epilogue
 // staging bytes per epilogue warp (TMA-store epilogues), 0 = direct global stores
 __host__ __device__ constexpr int epi_stage_bytes(int epi) {
   return epi == B200VIT_EPI_QKV_ROPE        ? 32 * 160
-         : epi == B200VIT_EPI_BIAS_RESIDUAL ? 2 * 4096
+         : epi == B200VIT_EPI_BIAS_RESIDUAL ? RESID_BUFS * 4096
          : epi == B200VIT_EPI_SWIGLU        ? 4096
          : epi == B200VIT_EPI_BIAS_GELU     ? 2 * 4096
                                             : 0;
@@ -151,10 +155,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
     static_assert(CW % 32 == 0, "32-column chunks");
 #pragma unroll
     for (int c = 0; c < CW; c += 32) {
-      const uint32_t buf = stg + ((c >> 5) & 1) * 4096;
+      const uint32_t buf = stg + ((c >> 5) % RESID_BUFS) * 4096;
       uint32_t v[32];
       tmem_ld32(taddr + c, v);
-      if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer (two chunks ago) has read it
+      if (lane == 0) bulk_wait_read<RESID_BUFS - 1>();  // the store that last used this buffer has read it
       __syncwarp();
       const int col = col0 + c;
       tmem_ld_wait();
