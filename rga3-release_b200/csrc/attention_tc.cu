@@ -267,30 +267,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
           }
         }
       } else {
+        // Independent streams: issue whichever stream's next operation is ready (a blocked stream must not
+        // hold up the other one's P V).  Per stream the order is QK(0) PV(0) QK(1) PV(1) ...
+        int next_op[QTILES];  // 2*i = QK(i), 2*i+1 = PV(i)
 #pragma unroll
-        for (int t = 0; t < QTILES; ++t) {
-          mbar_wait(&q_full[t], 0);
-          mbar_wait(&k_full[t], 0);
-          tc_fence_after();
-          issue_qk(t, 0);
-          umma_commit(&k_empty[t]);
-          if (nblk == 1) umma_commit(&q_empty[t]);
-        }
-        for (int i = 0; i < n_iter; ++i) {
-          const bool more = i + 1 < n_iter;
+        for (int t = 0; t < QTILES; ++t) next_op[t] = 0;
+        int remaining = QTILES * 2 * n_iter;
+        const long long t0 = clock64();
+        while (remaining > 0) {
+          bool progressed = false;
 #pragma unroll
           for (int t = 0; t < QTILES; ++t) {
-            mbar_wait(&v_full[t], i & 1);
-            issue_pv(t, i);
-            umma_commit(&v_empty[t]);
-            if (more) {
-              mbar_wait(&k_full[t], (i + 1) & 1);
-              if ((i + 1) % nblk == 0) mbar_wait(&q_full[t], ((i + 1) / nblk) & 1);
+            const int op = next_op[t];
+            if (op >= 2 * n_iter) continue;
+            const int i = op >> 1;
+            if ((op & 1) == 0) {  // QK(i): operands landed (S(t) is free: PV(i-1) was issued after p_full(i-1))
+              if (!mbar_test(&k_full[t], i & 1)) continue;
+              if (i % nblk == 0 && !mbar_test(&q_full[t], (i / nblk) & 1)) continue;
               tc_fence_after();
-              issue_qk(t, i + 1);
+              issue_qk(t, i);
               umma_commit(&k_empty[t]);
-              if ((i + 1) % nblk == nblk - 1) umma_commit(&q_empty[t]);
+              if (i % nblk == nblk - 1) umma_commit(&q_empty[t]);
+            } else {              // PV(i): V landed, softmax done, O(t) drained
+              if (!mbar_test(&v_full[t], i & 1) || !mbar_test(&p_full[t], i & 1) || !mbar_test(&o_empty[t], (i & 1) ^ 1))
+                continue;
+              issue_pv(t, i);  // its own waits succeed immediately
+              umma_commit(&v_empty[t]);
             }
+            next_op[t] = op + 1;
+            --remaining;
+            progressed = true;
+          }
+          if (!progressed && clock64() - t0 > 8000000000ll) {
+            printf("b200vit: attention scheduler timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
+            __trap();
           }
         }
       }
@@ -358,24 +368,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
       const float m_new = fmaxf(m_run, mx * scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // nothing valid so far: p = 0, no NaN
       const float alpha = ex2_approx(m_run - m_use);           // m_run = -inf -> 0
-      // ---- pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V); one 64-wide sub-tile per trip
+      // ---- pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V), 32 columns per trip
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < KVB; c += 64) {
-        const uint32_t sub = pbuf + (c >> 6) * T64_BYTES;
-        if (__all_sync(0xffffffffu, c + 64 <= lo || c >= hi)) {
+      for (int c = 0; c < KVB; c += 32) {
+        const uint32_t sub = pbuf + (c >> 6) * T64_BYTES;  // 64-wide sub-tile
+        const int j0 = (c & 63) >> 3;                      // first 16-byte chunk of this 32-column group
+        if (__all_sync(0xffffffffu, c + 32 <= lo || c >= hi)) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) st_shared_v4(swz128(sub, r, q), 0u, 0u, 0u, 0u);
+          for (int q = 0; q < 4; ++q) st_shared_v4(swz128(sub, r, j0 + q), 0u, 0u, 0u, 0u);
           continue;
         }
-        uint32_t v[64];
-        tmem_ld32(ts + c, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_ld32(ts + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        uint32_t v[32];
+        tmem_ld32(ts + c, v);
         tmem_ld_wait();
-        uint32_t pk[32];
-        if (__all_sync(0xffffffffu, c >= lo && c + 64 <= hi)) {
+        uint32_t pk[16];
+        if (__all_sync(0xffffffffu, c >= lo && c + 32 <= hi)) {
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
+          for (int i = 0; i < 32; i += 2) {
             const float p0 = ex2_approx(__uint_as_float(v[i]) * scale_log2 - m_use);
             const float p1 = ex2_approx(__uint_as_float(v[i + 1]) * scale_log2 - m_use);
             sum += p0 + p1;
@@ -383,7 +393,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
+          for (int i = 0; i < 32; i += 2) {
             float p0 = ex2_approx(__uint_as_float(v[i]) * scale_log2 - m_use);
             float p1 = ex2_approx(__uint_as_float(v[i + 1]) * scale_log2 - m_use);
             p0 = (c + i >= lo && c + i < hi) ? p0 : 0.f;
@@ -393,8 +403,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
           }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          st_shared_v4(swz128(sub, r, q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          st_shared_v4(swz128(sub, r, j0 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
