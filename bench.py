@@ -390,7 +390,11 @@ def main():
                     "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": launches * args.steps, "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the ncu --set full
+                         # capture in profiles/r01_ncu_gateup_gemm_full.csv (algorithmic minimum 95 MB: A 21 + W 17.7 +
+                         # out 56.6; part of the output is still in L2 when the kernel ends)
+                         "traffic": 57.4e6 if dom == "gateup_swiglu" else None, "traffic_unit": "bytes/launch",
                          "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                          "flops_per_launch": dom_flops, "avg_launch_ms": dom_ms},
             "kernel_ms_per_step": breakdown,

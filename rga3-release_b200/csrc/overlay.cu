@@ -159,6 +159,68 @@ overlay_patchify_kernel(const __grid_constant__ PatchParams p, const __grid_cons
   *reinterpret_cast<uint4*>(out + row * p.cols + col0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
+// Strip version for the Qwen2.5-VL geometry (patch 14, temporal 2, merge 2): a block owns G consecutive
+// merge groups of one (t, merge-row) strip -- 28 rows x 28G pixels x 2 frames in, 4G consecutive patch
+// rows out.  Pixels are visited in raster order (byte loads of consecutive lanes fall in the same
+// sectors, the overlay is evaluated once per pixel instead of once per channel), values are scattered
+// into the patch layout in shared memory and leave as one contiguous, 16-byte-vectorised block.
+constexpr int SP = 14, STPS = 2, SMG = 2, SG = 2;           // geometry, groups per block
+constexpr int SCOLS = 3 * STPS * SP * SP;                   // 1176
+constexpr int STRIP_SMEM = SG * SMG * SMG * SCOLS * 2;      // 18,816 B
+
+template <bool HAS_OVERLAY>
+__global__ void __launch_bounds__(256)
+overlay_patchify_strip_kernel(const __grid_constant__ PatchParams p, const __grid_constant__ OverlayParams ov,
+                              __nv_bfloat16* __restrict__ out) {
+  griddep_launch_dependents();
+  extern __shared__ __align__(16) uint8_t strip_raw[];
+  uint16_t* out_s = reinterpret_cast<uint16_t*>(strip_raw);
+  __shared__ uint16_t lut[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = c_norm_lut[i];
+  __syncthreads();
+  griddep_wait();  // the output buffer may still be read by the previous forward's patch-embed GEMM
+  const int gw2 = p.gw / SMG, gh2 = p.gh / SMG;
+  const int bw0 = blockIdx.x * SG;
+  const int groups = min(SG, gw2 - bw0);
+  const int bh = blockIdx.y;
+  const int tt = blockIdx.z + static_cast<int>(p.row_base / (static_cast<int64_t>(p.gh) * p.gw));  // absolute temporal index
+  constexpr int RH = SP * SMG;          // 28 pixel rows per strip
+  const int rw = groups * RH;           // pixel columns of this block
+  const int npx = STPS * RH * rw;
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < npx; idx += blockDim.x) {
+    const int tp = idx / (RH * rw);
+    const int rem = idx - tp * (RH * rw);
+    const int yy = rem / rw, xx = rem - yy * rw;
+    const int f = min(tt * STPS + tp, p.t_total - 1);  // odd T: repeat the last frame (HF videoproc :245-249)
+    const int y = bh * RH + yy, x = bw0 * RH + xx;
+    const uint8_t* px = p.frames + ((static_cast<size_t>(f - p.frame_base) * p.h + y) * p.w + x) * 3;
+    uint32_t d0 = __ldg(px), d1 = __ldg(px + 1), d2 = __ldg(px + 2);
+    if (HAS_OVERLAY) {
+      const uint32_t sv = overlay_at(ov, ov.ops[f - p.frame_base], p.h, p.w, y, x);
+      const uint32_t a = sv >> 24;
+      if (a) {
+        d0 = composite_ch(d0, sv & 0xffu, a);
+        d1 = composite_ch(d1, (sv >> 8) & 0xffu, a);
+        d2 = composite_ch(d2, (sv >> 16) & 0xffu, a);
+      }
+    }
+    const int g = xx / RH, xg = xx - g * RH;
+    const int mi = (yy / SP) * SMG + xg / SP;
+    const int ph = yy % SP, pw = xg % SP;
+    uint16_t* dst = out_s + (g * SMG * SMG + mi) * SCOLS + tp * SP * SP + ph * SP + pw;
+    dst[0] = lut[d0];
+    dst[STPS * SP * SP] = lut[256 + d1];
+    dst[2 * STPS * SP * SP] = lut[512 + d2];
+  }
+  __syncthreads();
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.z) * gh2 + bh) * gw2 * SMG * SMG + static_cast<int64_t>(bw0) * SMG * SMG;
+  uint4* gdst = reinterpret_cast<uint4*>(out + row0 * SCOLS);
+  const uint4* ssrc = reinterpret_cast<const uint4*>(out_s);
+  const int nvec = groups * SMG * SMG * SCOLS * 2 / 16;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) gdst[i] = ssrc[i];
+}
+
 __global__ void __launch_bounds__(256)
 overlay_composite_kernel(const __grid_constant__ PatchParams p, const __grid_constant__ OverlayParams ov,
                          uint8_t* __restrict__ out) {
@@ -302,10 +364,24 @@ int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov,
       const int64_t threads = p.rows * (cols / 8);
       const int grid = static_cast<int>((threads + 255) / 256);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_bf16) + p.row_base * cols;
-      if (ov != nullptr && ov->h_ops != nullptr)
+      const bool has_ov = ov != nullptr && ov->h_ops != nullptr;
+      if (patch == SP && tps == STPS && merge == SMG) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          B200_CUDA_OK(cudaFuncSetAttribute(overlay_patchify_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
+          B200_CUDA_OK(cudaFuncSetAttribute(overlay_patchify_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
+          attr_set = true;
+        }
+        const dim3 sgrid((gw / SMG + SG - 1) / SG, gh / SMG, nf_pad / tps);
+        if (has_ov)
+          B200_CUDA_OK(launch_kernel(overlay_patchify_strip_kernel<true>, sgrid, dim3(256), STRIP_SMEM, stream, 1, p, o, dst));
+        else
+          B200_CUDA_OK(launch_kernel(overlay_patchify_strip_kernel<false>, sgrid, dim3(256), STRIP_SMEM, stream, 1, p, o, dst));
+      } else if (has_ov) {
         B200_CUDA_OK(launch_kernel(overlay_patchify_kernel<true>, dim3(grid), dim3(256), 0, stream, 1, p, o, dst));
-      else
+      } else {
         B200_CUDA_OK(launch_kernel(overlay_patchify_kernel<false>, dim3(grid), dim3(256), 0, stream, 1, p, o, dst));
+      }
     }
     if (out_u8) {
       const int64_t npx = static_cast<int64_t>(nf) * fr.h * fr.w;
