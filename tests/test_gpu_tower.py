@@ -179,3 +179,41 @@ def test_ragged_grid_7b_vs_hf_fp32():
     out = t(x, torch.tensor(grid))
     cos, rel = parity(out, ref)
     assert cos >= COS_MIN and rel <= REL_MAX, (cos, rel)
+
+
+def test_drop_in_inside_hf_qwen2_5_vl_model():
+    """SURVEY.md 8b / cfg 5 boundary: swap the tower inside a full Qwen2.5-VL model (the class UniGRModel subclasses,
+    /root/reference/model/qwen_2_5_vl_sam2.py:104) with `install()` and run the model's own forward: HF's
+    get_video_features must accept our module (dtype/device attributes, .pooler_output) and the prefill logits must
+    agree with the stock tower's."""
+    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+    vc = dict(hf_ref.CFG_SMALL)
+    vc["out_hidden_size"] = 256
+    cfg = Qwen2_5_VLConfig(
+        text_config=dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                         intermediate_size=512, vocab_size=1000, max_position_embeddings=4096,
+                         rope_scaling={"type": "mrope", "mrope_section": [8, 12, 12]}),
+        vision_config=vc, video_token_id=990, image_token_id=991, vision_start_token_id=992, vision_end_token_id=993)
+    torch.manual_seed(0)
+    model = Qwen2_5_VLForConditionalGeneration(cfg).eval().to(DEV).to(torch.bfloat16)
+    with torch.no_grad():  # non-trivial norm weights / biases in the tower
+        for n, p_ in model.model.visual.named_parameters():
+            if n.endswith("bias"):
+                p_.normal_(0, 0.02)
+            elif "norm" in n or "ln_q" in n:
+                p_.copy_(1 + 0.1 * torch.randn_like(p_))
+    grid = torch.tensor([[2, 8, 12], [1, 6, 10]], device=DEV)
+    m = int(grid.prod(-1).sum())
+    nvis = [int(g.prod()) // 4 for g in grid]
+    ids = [1, 2]
+    for n in nvis:
+        ids += [992] + [990] * n + [993]
+    ids = torch.tensor([ids + [5, 6, 7]], device=DEV)
+    pv = torch.randn(m, 1176, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)).to(torch.bfloat16)
+    with torch.no_grad():
+        ref = model(input_ids=ids, pixel_values_videos=pv, video_grid_thw=grid).logits.float()
+        tower = vit.install(model)
+        assert isinstance(model.model.visual, vit.B200VisionTower) and tower.dtype == torch.bfloat16
+        out = model(input_ids=ids, pixel_values_videos=pv, video_grid_thw=grid).logits.float()
+    cos, rel = parity(out, ref)
+    assert cos >= 0.999 and rel <= 3e-2, (cos, rel)   # both sides are bf16 end to end here
