@@ -106,62 +106,64 @@ def random_state_dict_gpu(tower, seed=0):
 
 
 # ----------------------------------------------------------------------------- clocks
+_SAMPLER_SRC = r"""
+import sys, time, pynvml as nv
+idx, interval = int(sys.argv[1]), float(sys.argv[2])
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(idx)
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)   # ~4 ms per call: once, up front
+while True:
+    try:
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(r), flush=True)
+    time.sleep(interval)
+"""
+
+
 class ClockSampler:
-    """SM clock / power / throttle reasons DURING the timed region, read in-process through NVML
-    (nvidia_ml_py) every 50 ms; falls back to one `nvidia-smi` query per sample if NVML is unavailable."""
+    """SM clock / power / throttle reasons DURING the timed region, read through NVML in a SEPARATE process
+    (a sampling thread inside the benchmark process slowed multi-GPU steps by 15-25 %: its NVML calls contend
+    with the launching thread; measured)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index, interval=0.1):
-        self.idx, self.rows, self.stop_flag, self.thread, self.h = gpu_index, [], False, None, None
-        self.interval = interval   # NVML queries perturb the GPU for ~ms: a handful of samples per region, not a stream
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
-            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
-        except Exception:
-            self.nv = None
-
-    def _sample(self):
-        if self.nv is not None:
-            nv, h = self.nv, self.h
-            try:
-                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-            except Exception:
-                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-            return (nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
-                    nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons))
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
-        o = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                           capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-        return float(o[0]), float(o[1]), float(o[2]), int(o[3].strip(), 16)
-
-    def _loop(self):
-        while not self.stop_flag:
-            try:
-                self.rows.append((time.time(),) + tuple(self._sample()))
-            except Exception:
-                pass
-            time.sleep(self.interval)
+        self.rows, self.proc, self.max_mhz = [], None, None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        self.interval = interval
 
     def start(self):
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.phys), str(self.interval)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline().split()      # blocks until NVML is up in the child
+            self.max_mhz = float(first[1]) if len(first) == 2 and first[0] == "max" else None
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = line.split()
+            if len(f) == 4:
+                self.rows.append((float(f[0]), float(f[1]), float(f[2]), int(f[3])))
 
     def stop(self, t0, t1):
-        self.stop_flag = True
-        if self.thread is not None:
-            self.thread.join(timeout=2)
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
         rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-1:]
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock sample inside the timed region"]}
         bits = 0
         for r in rows:
-            bits |= r[4]
-        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(rows[0][2]),
+            bits |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(rows),
-                "power_w_max": float(max(r[3] for r in rows)), "source": "nvml" if self.nv is not None else "nvidia-smi"}
+                "power_w_max": float(max(r[2] for r in rows)), "source": "nvml (separate process)"}
 
 
 # ----------------------------------------------------------------------------- reference (CPU) arm
@@ -277,10 +279,11 @@ def main():
     torch.cuda.synchronize(dev)
     est_total = (time.perf_counter() - t_w) * args.steps
     barrier()
-    sampler = ClockSampler(local_rank, interval=min(max(est_total / 5.0, 0.1), 1.0))
-    if rank == 0:
+    # NVML reads on a GPU that is inside an NCCL-coupled loop cost every rank a few ms each (measured at N = 2:
+    # 10.97 ms/step unsampled, 12.6 with 4 samples in 0.36 s): with N > 1 take two samples per region, not a stream
+    sampler = ClockSampler(local_rank, interval=min(max(est_total / (5.0 if world == 1 else 2.5), 0.1), 2.0))
+    if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):
         sampler.start()
-        time.sleep(0.1)
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
