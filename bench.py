@@ -245,7 +245,9 @@ def main():
     frames_host = synthetic_frames(T_FRAMES, H, W, clip_id=rank).pin_memory()
     frames_dev = frames_host.to(dev)
     out = torch.empty(m // 4, CFG_7B["out_hidden_size"], dtype=torch.bfloat16, device=dev)
+    outs = [out, torch.empty_like(out)]
     gather_list = [torch.empty_like(out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gather_lists = [gather_list, [torch.empty_like(out) for _ in range(world)] if gather_list is not None else None]
 
     do_gather = world > 1 and not os.environ.get("BENCH_NO_GATHER")
     gmode = os.environ.get("BENCH_GATHER", "gather")
@@ -259,10 +261,29 @@ def main():
         else:
             dist.all_gather_into_tensor(ag_buf, t)
 
+    pending = [None, None]
+    step_no = [0]
+
     def step_resident():
-        tower.forward_frames(frames_dev, overlay, out=out)
+        """One clip through the path; with N > 1 the merged tokens go to rank 0 on NCCL's stream while the next
+        clip is already being computed (two output buffers; a buffer is reused only after its gather finished)."""
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if pending[b] is not None:
+            pending[b].wait()          # stream-level wait, the host does not block
+            pending[b] = None
+        tower.forward_frames(frames_dev, overlay, out=outs[b])
         if do_gather:
-            gather_out(out)
+            if gmode == "gather":
+                pending[b] = dist.gather(outs[b], gather_lists[b], dst=0, async_op=True)
+            else:
+                gather_out(outs[b])
+
+    def drain():
+        for b in (0, 1):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -276,6 +297,7 @@ def main():
     torch.cuda.synchronize(dev)
     t_w = time.perf_counter()
     step_resident()
+    drain()
     torch.cuda.synchronize(dev)
     est_total = (time.perf_counter() - t_w) * args.steps
     barrier()
@@ -289,6 +311,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_resident()
+    drain()
     e1.record()
     barrier()
     t_wall1 = time.time()
