@@ -92,8 +92,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int QTILES, int NKV, int NQ, bool SHARED_KV>
 __global__ void __launch_bounds__(AttnCfg<QTILES, NKV, NQ, SHARED_KV>::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
-               const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, __nv_bfloat16* __restrict__ out,
-               int m_rows, int heads, int heads_per_cta, float scale_log2) {
+               const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap to16,
+               const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, int m_rows, int heads,
+               int heads_per_cta, float scale_log2) {
   using L = AttnCfg<QTILES, NKV, NQ, SHARED_KV>;
   griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -123,6 +124,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm64);
     tma_prefetch_desc(&tm16);
+    tma_prefetch_desc(&to64);
+    tma_prefetch_desc(&to16);
     for (int b = 0; b < L::NQBAR; ++b) {
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
@@ -289,7 +292,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
               umma_commit(&k_empty[t]);
               if (i % nblk == nblk - 1) umma_commit(&q_empty[t]);
             } else {              // PV(i): V landed, softmax done, O(t) drained
-              if (!mbar_test(&v_full[t], i & 1) || !mbar_test(&p_full[t], i & 1) || !mbar_test(&o_empty[t], (i & 1) ^ 1))
+              // p_full is the one that is normally still pending: test it first so an idle poll costs one probe
+              if (!mbar_test(&p_full[t], i & 1) || !mbar_test(&v_full[t], i & 1) || !mbar_test(&o_empty[t], (i & 1) ^ 1))
                 continue;
               issue_pv(t, i);  // its own waits succeed immediately
               umma_commit(&v_empty[t]);
@@ -298,6 +302,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
             --remaining;
             progressed = true;
           }
+          if (!progressed) __nanosleep(40);  // do not steal issue slots from the softmax warps on this sub-partition
           if (!progressed && clock64() - t0 > 8000000000ll) {
             printf("b200vit: attention scheduler timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
             __trap();
@@ -323,26 +328,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
     auto accumulate_block = [&](int i, float alpha) {
       mbar_wait(&o_full[t], i & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < HD; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(to + c, v);
+      {
+        uint32_t v[48];  // 48 + 32 columns: two TMEM round trips instead of five
+        tmem_ld32(to, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld16(to + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
         tmem_ld_wait();
 #pragma unroll
-        for (int i2 = 0; i2 < 16; ++i2) o[c + i2] = o[c + i2] * alpha + __uint_as_float(v[i2]);
+        for (int i2 = 0; i2 < 48; ++i2) o[i2] = o[i2] * alpha + __uint_as_float(v[i2]);
+        tmem_ld32(to + 48, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int i2 = 0; i2 < 32; ++i2) o[48 + i2] = o[48 + i2] * alpha + __uint_as_float(v[i2]);
       }
       tc_fence_before();
       mbar_arrive(&o_empty[t]);
     };
 
+#ifdef B200_ATTN_TIMING
+    long long tstamp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+    const bool trec = (blockIdx.x == 1 && blockIdx.y == 0 && warp == 2 && lane == 0);
+#define TSTAMP(k) do { long long _n = clock64(); tstamp[k] += _n - tprev; tprev = _n; } while (0)
+#else
+#define TSTAMP(k)
+#endif
     for (int hl = 0; hl < n_hl; ++hl) {
     m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
 #pragma unroll
     for (int i2 = 0; i2 < HD; ++i2) o[i2] = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int it = hl * nblk + j;  // flattened iteration (barrier phases)
+      TSTAMP(0);
       mbar_wait(&s_full[t], it & 1);
       tc_fence_after();
+      TSTAMP(1);
       // valid kv range of this row inside the block, in columns [0, 128)
       const int kv0 = tile.kv_row0 + j * KVB;
       const int lo = max(bd.x - kv0, 0), hi = min(bd.y - kv0, KVB);
@@ -365,10 +384,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
           for (int i = 0; i < 64; ++i) mx = fmaxf(mx, (c + i >= lo && c + i < hi) ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
+      TSTAMP(2);
       const float m_new = fmaxf(m_run, mx * scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // nothing valid so far: p = 0, no NaN
       const float alpha = ex2_approx(m_run - m_use);           // m_run = -inf -> 0
       // ---- pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V), 32 columns per trip
+      if (lane == 0) bulk_wait_read<0>();  // the previous head's output store (staged in this P region) has drained
+      __syncwarp();
       float sum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < KVB; c += 32) {
@@ -408,27 +430,50 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
+      TSTAMP(3);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      TSTAMP(4);
       // the previous block's P V has long finished: fold it in while the tensor core works on this one
       if (j >= 1) accumulate_block(it - 1, alpha_prev);
       alpha_prev = alpha;
     }
     accumulate_block(hl * nblk + nblk - 1, alpha_prev);
+    TSTAMP(5);
 
-    if (row < m_rows && bd.y > bd.x) {
-      const float inv = 1.f / l_run;
+    {
+      // O -> bf16 -> this warp's own rows of the (now idle) P buffer -> two TMA stores (64 + 16 columns).
+      // A thread owns a row, so direct global stores would be 32 scattered sectors per instruction.
+      const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
       const int head = SHARED_KV ? head0 + hl : head0 + hl * QTILES + t;
-      __nv_bfloat16* op = out + static_cast<size_t>(row) * D + head * HD;
+      const uint32_t stg64 = pbuf + quad * 4096;               // rows quad*32.. of sub-tile 0 (1024-aligned)
+      const uint32_t stg16 = pbuf + T64_BYTES + quad * 4096;   // same rows of sub-tile 1
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
-        *reinterpret_cast<uint4*>(op + c) =
-            make_uint4(pack_bf16x2(o[c] * inv, o[c + 1] * inv), pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv),
-                       pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
+      for (int c = 0; c < 64; c += 8)
+        st_shared_v4(swz128(stg64, lane, c >> 3), pack_bf16x2(o[c] * inv, o[c + 1] * inv), pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv),
+                     pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
+#pragma unroll
+      for (int c = 64; c < HD; c += 8)
+        st_shared_v4(stg16 + lane * 32 + (c - 64) * 2, pack_bf16x2(o[c] * inv, o[c + 1] * inv),
+                     pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv), pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv),
+                     pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = tile.q_row0 + (SHARED_KV ? t * QT : 0) + quad * 32;
+        tma_store_2d(&to64, stg64, head * HD, row0);        // rows >= m_rows are clipped by the tensor map
+        tma_store_2d(&to16, stg16, head * HD + 64, row0);
+        bulk_commit();
       }
     }
+    TSTAMP(6);
     }  // heads of this CTA
+    if (lane == 0) bulk_wait<0>();  // output stores have landed before the CTA exits
+#ifdef B200_ATTN_TIMING
+    if (trec) printf("attn timing (cycles, %d head-iters): other %lld | wait_s %lld | pass1 %lld | pass2 %lld | fence+arrive %lld | wait_o+acc %lld | store %lld\n",
+                     n_hl, tstamp[0], tstamp[1], tstamp[2], tstamp[3], tstamp[4], tstamp[5], tstamp[6]);
+#endif
   }
 
   tc_fence_before();
@@ -440,8 +485,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 }
 
 template <int QTILES, int NKV, int NQ, bool SHARED_KV>
-int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, const int2* bd, __nv_bfloat16* o, int m_rows,
-                   int heads, int hpc, float scale_log2, cudaStream_t stream) {
+int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, const int2* bd, int m_rows, int heads, int hpc,
+                   float scale_log2, cudaStream_t stream) {
   using L = AttnCfg<QTILES, NKV, NQ, SHARED_KV>;
   auto kern = attn_tc_kernel<QTILES, NKV, NQ, SHARED_KV>;
   static bool attr = false;
@@ -449,8 +494,8 @@ int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, 
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
     attr = true;
   }
-  B200_CUDA_OK(launch_kernel(kern, dim3(n_tiles, heads / hpc), dim3(L::THREADS), L::BYTES, stream, 1, g.tm64, g.tm16, d_tiles, bd,
-                             o, m_rows, heads, hpc, scale_log2));
+  B200_CUDA_OK(launch_kernel(kern, dim3(n_tiles, heads / hpc), dim3(L::THREADS), L::BYTES, stream, 1, g.tm64, g.tm16, g.to64,
+                             g.to16, d_tiles, bd, m_rows, heads, hpc, scale_log2));
   return 0;
 }
 
@@ -486,22 +531,25 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
   AttnPrepared local;
   AttnPrepared& g = cache ? *cache : local;
   const int D = heads * HD;
-  if (!(g.valid && g.qkv == qkv && g.m_rows == m_rows && g.heads == heads)) {
+  if (!(g.valid && g.qkv == qkv && g.out == out && g.m_rows == m_rows && g.heads == heads)) {
     int rc = make_tmap_2d(&g.tm64, qkv, m_rows, 3 * D, 3 * D, 2, 128, 64, 128);
     if (rc) return rc;
     rc = make_tmap_2d(&g.tm16, qkv, m_rows, 3 * D, 3 * D, 2, 128, 16, 32);
     if (rc) return rc;
-    g.qkv = qkv, g.m_rows = m_rows, g.heads = heads, g.valid = true;
+    rc = make_tmap_2d(&g.to64, out, m_rows, D, D, 2, 32, 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&g.to16, out, m_rows, D, D, 2, 32, 16, 0);
+    if (rc) return rc;
+    g.qkv = qkv, g.out = out, g.m_rows = m_rows, g.heads = heads, g.valid = true;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int2* bd = reinterpret_cast<const int2*>(d_bounds);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (rows_per_tile == 256)
-    return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, o, m_rows, heads, 1, scale_log2, stream);
+    return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
   if (rows_per_tile != 128) return fail(B200VIT_EINVAL, "attention: rows_per_tile must be 128 or 256");
   (void)max_blocks;
   if (heads % 2 != 0)  // odd head count: single stream, K/V double-buffered
-    return launch_variant<1, 2, 2, true>(g, d_tiles, n_tiles, bd, o, m_rows, heads, 1, scale_log2, stream);
+    return launch_variant<1, 2, 2, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
   // window layers: two heads in flight per CTA; walk as many head pairs per CTA as keep ~one CTA per SM
   int hpc = 2;
   const int sms = device_sm_count();
@@ -510,7 +558,7 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
       hpc = c;
       break;
     }
-  return launch_variant<2, 1, 1, false>(g, d_tiles, n_tiles, bd, o, m_rows, heads, hpc, scale_log2, stream);
+  return launch_variant<2, 1, 1, false>(g, d_tiles, n_tiles, bd, m_rows, heads, hpc, scale_log2, stream);
 }
 
 }  // namespace b200

@@ -57,8 +57,10 @@ struct AttnTile {
 struct AttnPrepared {  // host memo of the two tensor maps over the qkv buffer
   bool valid = false;
   const void* qkv = nullptr;
+  const void* out = nullptr;
   int m_rows = 0, heads = 0;
-  CUtensorMap tm64, tm16;
+  CUtensorMap tm64, tm16;  // loads from the qkv buffer
+  CUtensorMap to64, to16;  // stores to the attention output
 };
 void build_attn_tiles(const std::vector<int32_t>& cu, int m_rows, int rows_per_tile, std::vector<AttnTile>& tiles,
                       std::vector<int32_t>& bounds);
