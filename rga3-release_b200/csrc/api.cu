@@ -25,7 +25,6 @@ struct b200vit_plan {
   std::vector<int32_t> cu_window, cu_full, row_map, merge_map, pos_ids;
   std::vector<float> rope_cos, rope_sin;  // [M, head_dim/2] in window order
   std::vector<uint32_t> rope_packed;      // same table as fp16 (cos, sin) pairs -- what the QKV epilogue reads
-  std::vector<AttnWork> work_window, work_full;          // legacy mma.sync attention
   std::vector<AttnTile> tiles_window, tiles_full;         // tcgen05 attention
   std::vector<int32_t> bounds_window, bounds_full;        // per-row [lo, hi) of the row's segment
   int maxblk_window = 0, maxblk_full = 0;
@@ -39,8 +38,6 @@ struct b200vit_plan {
   int32_t* d_row_map = nullptr;
   int32_t* d_merge_map = nullptr;
   uint32_t* d_rope = nullptr;
-  AttnWork* d_work_window = nullptr;
-  AttnWork* d_work_full = nullptr;
   AttnTile* d_tiles_window = nullptr;
   AttnTile* d_tiles_full = nullptr;
   int32_t* d_bounds_window = nullptr;
@@ -56,14 +53,6 @@ struct b200vit_plan {
 namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-void build_work(const std::vector<int32_t>& cu, std::vector<AttnWork>& out) {
-  out.clear();
-  for (size_t i = 0; i + 1 < cu.size(); ++i) {
-    const int s = cu[i], e = cu[i + 1];
-    for (int q0 = s; q0 < e; q0 += 64) out.push_back(AttnWork{q0, std::min(64, e - q0), s, e - s});
-  }
-}
 
 // HF modeling_qwen2_5_vl.py:411-451 (get_window_index) + :476 (unique_consecutive)
 void build_window_index(b200vit_plan& p) {
@@ -153,8 +142,6 @@ int ensure_uploaded(b200vit_plan* p) {
   if ((rc = upload(&p->d_row_map, p->row_map))) return rc;
   if ((rc = upload(&p->d_merge_map, p->merge_map))) return rc;
   if ((rc = upload(&p->d_rope, p->rope_packed))) return rc;
-  if ((rc = upload(&p->d_work_window, p->work_window))) return rc;
-  if ((rc = upload(&p->d_work_full, p->work_full))) return rc;
   if ((rc = upload(&p->d_tiles_window, p->tiles_window))) return rc;
   if ((rc = upload(&p->d_tiles_full, p->tiles_full))) return rc;
   if ((rc = upload(&p->d_bounds_window, p->bounds_window))) return rc;
@@ -187,15 +174,6 @@ struct Prof {
     p->ev_used += 2;
   }
 };
-
-bool legacy_attention() {  // B200VIT_ATTN=legacy selects the mma.sync kernel (A/B comparison only)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200VIT_ATTN");
-    v = (e != nullptr && std::strcmp(e, "legacy") == 0) ? 1 : 0;
-  }
-  return v == 1;
-}
 
 // Keep the fp32 residual stream resident in L2 across the ~250 MB of other traffic each block generates:
 // x is read by both RMSNorms and read-modify-written by both residual GEMMs of every block (SURVEY.md 8d:
@@ -302,8 +280,6 @@ int b200vit_plan_create(const int64_t* h_grid_thw, int n_grids, const b200vit_cf
   p->merge_map.resize(p->window_index.size());
   for (size_t i = 0; i < p->window_index.size(); ++i) p->merge_map[i] = static_cast<int32_t>(p->window_index[i]);
   build_rope(*p);
-  build_work(p->cu_window, p->work_window);
-  build_work(p->cu_full, p->work_full);
   build_attn_tiles(p->cu_window, static_cast<int>(p->m), 128, p->tiles_window, p->bounds_window);
   build_attn_tiles(p->cu_full, static_cast<int>(p->m), 256, p->tiles_full, p->bounds_full);
   for (const AttnTile& t : p->tiles_window) p->maxblk_window = std::max(p->maxblk_window, t.n_kv_blocks);
@@ -329,8 +305,6 @@ void b200vit_plan_destroy(b200vit_plan* p) {
   cudaFree(p->d_row_map);
   cudaFree(p->d_merge_map);
   cudaFree(p->d_rope);
-  cudaFree(p->d_work_window);
-  cudaFree(p->d_work_full);
   cudaFree(p->d_tiles_window);
   cudaFree(p->d_tiles_full);
   cudaFree(p->d_bounds_window);
@@ -431,14 +405,10 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
     prof.end();
     prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
-    if (legacy_attention())
-      rc = launch_attention(qkv, attn, full ? p->d_work_full : p->d_work_window,
-                            static_cast<int>(full ? p->work_full.size() : p->work_window.size()), c.heads, stream);
-    else
-      rc = launch_attention_tc(qkv, attn, full ? p->d_tiles_full : p->d_tiles_window,
-                               static_cast<int>(full ? p->tiles_full.size() : p->tiles_window.size()), full ? 256 : 128,
-                               full ? p->maxblk_full : p->maxblk_window, full ? p->d_bounds_full : p->d_bounds_window, M,
-                               c.heads, stream, &p->attn_cache);
+    rc = launch_attention_tc(qkv, attn, full ? p->d_tiles_full : p->d_tiles_window,
+                             static_cast<int>(full ? p->tiles_full.size() : p->tiles_window.size()), full ? 256 : 128,
+                             full ? p->maxblk_full : p->maxblk_window, full ? p->d_bounds_full : p->d_bounds_window, M,
+                             c.heads, stream, &p->attn_cache);
     if (rc) return rc;
     prof.end();
     std::memset(&g, 0, sizeof(g));
@@ -545,18 +515,6 @@ int b200vit_attention(const void* d_qkv, void* d_out, const int32_t* h_cu_seqlen
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   std::vector<int32_t> cu(h_cu_seqlens, h_cu_seqlens + n_segments + 1);
   const int m_rows = cu.back();
-  if (legacy_attention()) {
-    std::vector<AttnWork> work;
-    build_work(cu, work);
-    if (work.empty()) return 0;
-    AttnWork* d_work = nullptr;
-    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_work), work.size() * sizeof(AttnWork)));
-    B200_CUDA_OK(cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(AttnWork), cudaMemcpyHostToDevice, stream));
-    rc = launch_attention(d_qkv, d_out, d_work, static_cast<int>(work.size()), heads, stream);
-    cudaStreamSynchronize(stream);  // test entry point: the work list is freed before returning
-    cudaFree(d_work);
-    return rc;
-  }
   std::vector<AttnTile> tiles;
   std::vector<int32_t> bounds;
   int max_len = 0;

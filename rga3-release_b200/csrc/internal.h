@@ -45,11 +45,6 @@ int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* c
 int launch_rmsnorm(const float* x, const float* w, void* out_bf16, int rows, int dim, float eps, cudaStream_t stream);
 int launch_cast_bf16(const void* in, int in_dtype, void* out, int64_t n, cudaStream_t stream);
 
-struct AttnWork {  // one CTA of the attention kernel: <= 64 query rows of one segment
-  int32_t q_start, q_len, kv_start, kv_len;
-};
-int launch_attention(const void* qkv, void* out, const AttnWork* d_work, int n_work, int heads, cudaStream_t stream);
-
 // tcgen05 attention (attention_tc.cu): one CTA = 128 query rows of one head
 struct AttnTile {
   int32_t q_row0, kv_row0, n_kv_blocks, pad;
