@@ -4,9 +4,9 @@ Python host side of libb200vit.so; see include/b200vit.h, DESIGN.md, INTEGRATION
 """
 from . import _lib
 from ._lib import B200VitError, lib
-from .module import B200VisionTower, install
+from .module import B200VisionTower, install, splice_span
 from .dist import gather_tokens, shard_clips, shard_slices
 from .overlay import FrameOp, OverlaySpec, shift_from_flow, stom_frame_ops
 
-__all__ = ["B200VisionTower", "install", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "lib", "shard_clips", "shard_slices", "gather_tokens",
+__all__ = ["B200VisionTower", "install", "splice_span", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "lib", "shard_clips", "shard_slices", "gather_tokens",
            "B200VitError"]

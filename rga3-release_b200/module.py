@@ -244,8 +244,12 @@ class B200VisionTower(nn.Module):
         return out
 
     @torch.no_grad()
-    def forward(self, hidden_states: torch.Tensor, grid_thw, output_last_hidden_state: bool = False, **kwargs):
-        """hidden_states: [M, C*tp*p*p] float (bf16/fp16/fp32), CUDA; grid_thw: [n,3]."""
+    def forward(self, hidden_states: torch.Tensor, grid_thw, output_last_hidden_state: bool = False,
+                out: Optional[torch.Tensor] = None, **kwargs):
+        """hidden_states: [M, C*tp*p*p] float (bf16/fp16/fp32), CUDA; grid_thw: [n,3].
+        `out` (optional): contiguous [M/4, out_hidden] bf16/fp32 destination, e.g. the placeholder rows of the LLM's
+        `inputs_embeds` (see `splice_span`): the merger epilogue then writes the visual tokens in place and HF's
+        boolean-mask `masked_scatter` (modeling_qwen2_5_vl.py:1309-1315) becomes unnecessary."""
         if not hidden_states.is_cuda:
             raise ValueError("B200VisionTower.forward: hidden_states must be a CUDA tensor (no CPU path)")
         plan = self.plan_for(grid_thw)
@@ -262,9 +266,14 @@ class B200VisionTower(nn.Module):
             _lib.check(_lib.lib().b200vit_cast_to_bf16(x.data_ptr(), code, xb.data_ptr(), x.numel(), stream), "cast")
             x = xb
         out_dtype = torch.float32 if self.output_fp32 else self._dtype
-        if self.use_cuda_graph and not output_last_hidden_state:
+        if self.use_cuda_graph and not output_last_hidden_state and out is None:
             return self._wrap(self._graph_forward(plan, x, out_dtype), None)
-        out = torch.empty(plan.m // self.spatial_merge_unit, self.out_hidden_size, dtype=out_dtype, device=x.device)
+        shape = (plan.m // self.spatial_merge_unit, self.out_hidden_size)
+        if out is None:
+            out = torch.empty(shape, dtype=out_dtype, device=x.device)
+        elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.bfloat16, torch.float32) \
+                or not out.is_cuda:
+            raise ValueError(f"out must be a contiguous CUDA bf16/fp32 tensor of shape {shape}")
         last = torch.empty(plan.m, self.hidden_size, dtype=torch.float32, device=x.device) if output_last_hidden_state else None
         self._run(plan, x, None, None, out, last)
         return self._wrap(out, last)
@@ -329,6 +338,21 @@ class B200VisionTower(nn.Module):
 
     def launches_per_forward(self, grid_thw, with_frames=False) -> int:
         return int(_lib.lib().b200vit_forward_launches(self.plan_for(grid_thw).handle, 1 if with_frames else 0))
+
+
+def splice_span(input_ids: torch.Tensor, token_id: int):
+    """(start, length) of the run of visual placeholder tokens in a [1, L] / [L] `input_ids`.
+    Qwen2.5-VL emits all placeholders of one video as one contiguous run (vision_start, N x video_token, vision_end), so
+    `tower(pixel_values, grid, out=inputs_embeds[0, start:start + length])` replaces get_video_features + masked_scatter.
+    Raises if the placeholders are not contiguous (several videos: call once per video with its own span)."""
+    ids = input_ids.reshape(-1)
+    pos = torch.nonzero(ids == token_id).reshape(-1)
+    if pos.numel() == 0:
+        raise ValueError("no visual placeholder tokens in input_ids")
+    start, length = int(pos[0]), int(pos.numel())
+    if int(pos[-1]) - start + 1 != length:
+        raise ValueError("visual placeholder tokens are not one contiguous run")
+    return start, length
 
 
 def install(model, **kw):

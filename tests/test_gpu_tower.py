@@ -217,3 +217,25 @@ def test_drop_in_inside_hf_qwen2_5_vl_model():
         out = model(input_ids=ids, pixel_values_videos=pv, video_grid_thw=grid).logits.float()
     cos, rel = parity(out, ref)
     assert cos >= 0.999 and rel <= 3e-2, (cos, rel)   # both sides are bf16 end to end here
+
+
+def test_splice_into_inputs_embeds_in_place():
+    """the merger epilogue writes straight into the LLM's inputs_embeds rows; result equals HF's
+    masked_scatter of the separately computed embeddings."""
+    t, cfg, sd = make_tower(hf_ref.CFG_SMALL)
+    grid = [[2, 8, 12]]
+    m, n_vis, hid = 192, 48, hf_ref.CFG_SMALL["out_hidden_size"]
+    x = torch.randn(m, 1176, generator=torch.Generator().manual_seed(3)).to(DEV)
+    ids = torch.tensor([[5, 6, 992] + [990] * n_vis + [993, 7, 8]], device=DEV)
+    emb = torch.randn(1, ids.shape[1], hid, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4)).to(torch.bfloat16)
+    ref_tokens = t(x, torch.tensor(grid))
+    mask = (ids == 990).unsqueeze(-1).expand_as(emb)
+    ref = emb.clone().masked_scatter(mask, ref_tokens)                       # HF modeling :1309-1315
+    start, length = vit.splice_span(ids, 990)
+    assert (start, length) == (3, n_vis)
+    t(x, torch.tensor(grid), out=emb[0, start:start + length])
+    assert torch.equal(emb, ref)
+    with pytest.raises(ValueError):
+        vit.splice_span(torch.tensor([990, 1, 990]), 990)
+    with pytest.raises(ValueError):
+        t(x, torch.tensor(grid), out=emb[0, :length - 1])
