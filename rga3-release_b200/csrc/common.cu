@@ -77,7 +77,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols,
   if (!fn) return fail(B200VIT_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail(B200VIT_EALIGN, "TMA base pointer must be 16-byte aligned");
   if ((pitch_elems * elem_bytes) % 16) return fail(B200VIT_EALIGN, "TMA row pitch must be a multiple of 16 bytes");
-  if (swizzle_bytes != 0 && swizzle_bytes != 32 && swizzle_bytes != 128) return fail(B200VIT_EINVAL, "unsupported TMA swizzle");
+  if (swizzle_bytes != 0 && swizzle_bytes != 32 && swizzle_bytes != 64 && swizzle_bytes != 128) return fail(B200VIT_EINVAL, "unsupported TMA swizzle");
   if (swizzle_bytes && box_cols * elem_bytes != swizzle_bytes) return fail(B200VIT_EINVAL, "swizzled TMA box must span the swizzle width");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch_elems) * elem_bytes};
@@ -85,7 +85,9 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols,
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE), CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200VIT_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string(int(r)) + ")");
   return 0;

@@ -41,7 +41,7 @@ struct GemmParams {
   const int32_t* row_map;
   const uint32_t* rope;  // [M, 40] half2 (cos, sin)
   int m, n, k, ldo, rope_cols;
-  int stream_k;  // 1: stream-K decomposition (BIAS_RESIDUAL only)
+  int stream_k;  // bit 0: stream-K decomposition (BIAS_RESIDUAL only); bit 1: no weight prefetch before the PDL wait
 };
 
 #ifndef B200_RESID_BUFS
@@ -394,30 +394,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_wait();  // set-up above overlapped the previous kernel's tail; its outputs are visible from here on
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  Each role executes
+  // griddepcontrol.wait itself before it touches memory the previous kernel produced (A operand, output buffer);
+  // the producer first prefetches the WEIGHT tiles of its first pipeline stages, which depend on nothing.
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer (every CTA) =====================
+      // phase 1 (before the dependency wait): arm the first stages and start their B (weight) loads
+      int pre = 0;
+      {
+        WorkIter w0(num_tiles, num_kb, unit, num_units, (p.stream_k & 1) != 0);
+        Segment s0;
+        while (!(p.stream_k & 2) && pre < STAGES && w0.next(s0)) {
+          const int n0 = (s0.tile % num_n) * BN + rank * C::BN_LOAD;
+          for (int kb = s0.kb0; kb < s0.kb1 && pre < STAGES; ++kb, ++pre) {
+            if constexpr (PAIR) {
+              const uint32_t lead_full = mapa_u32(smem_u32(&full[pre]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&full[pre], 2 * C::STAGE_BYTES);
+              tma_load_2d_pair(sB + pre * C::B_BYTES, &tma_b, lead_full, kb * BK, n0);
+            } else {
+              mbar_arrive_expect_tx(&full[pre], C::STAGE_BYTES);
+              tma_load_2d(sB + pre * C::B_BYTES, &tma_b, &full[pre], kb * BK, n0);
+            }
+          }
+        }
+      }
+      griddep_wait();
+      // phase 2: the regular ring; the first `pre` k-blocks only need their A tile
       int s = 0;
       uint32_t ph = 0;
-      WorkIter work(num_tiles, num_kb, unit, num_units, p.stream_k != 0);
+      int issued = 0;
+      WorkIter work(num_tiles, num_kb, unit, num_units, (p.stream_k & 1) != 0);
       Segment sg;
       while (work.next(sg)) {
         const int m0 = (sg.tile / num_n) * MT + rank * BM;
         const int n0 = (sg.tile % num_n) * BN + rank * C::BN_LOAD;
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++issued) {
+          const bool b_done = issued < pre;
+          if (!b_done) mbar_wait(&empty[s], ph ^ 1);
           if constexpr (PAIR) {
             const uint32_t lead_full = mapa_u32(smem_u32(&full[s]), 0);
-            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+            if (!b_done && rank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
             tma_load_2d_pair(sA + s * C::A_BYTES, &tma_a, lead_full, kb * BK, m0);
-            tma_load_2d_pair(sB + s * C::B_BYTES, &tma_b, lead_full, kb * BK, n0);
+            if (!b_done) tma_load_2d_pair(sB + s * C::B_BYTES, &tma_b, lead_full, kb * BK, n0);
             if (rank != 0) mbar_arrive_cluster(lead_full);
           } else {
-            mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+            if (!b_done) mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
             tma_load_2d(sA + s * C::A_BYTES, &tma_a, &full[s], kb * BK, m0);
-            tma_load_2d(sB + s * C::B_BYTES, &tma_b, &full[s], kb * BK, n0);
+            if (!b_done) tma_load_2d(sB + s * C::B_BYTES, &tma_b, &full[s], kb * BK, n0);
           }
           if (++s == STAGES) {
             s = 0;
@@ -433,17 +458,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      WorkIter work(num_tiles, num_kb, unit, num_units, p.stream_k != 0);
+      WorkIter work(num_tiles, num_kb, unit, num_units, (p.stream_k & 1) != 0);
       Segment sg;
+#ifdef B200_GEMM_TIMING
+      long long t_acc = 0, t_full = 0, t_issue = 0, t_prev = clock64(), t_start = t_prev;
+      int n_seg = 0, n_kb = 0;
+#define GSTAMP(v) do { long long _n = clock64(); v += _n - t_prev; t_prev = _n; } while (0)
+#else
+#define GSTAMP(v)
+#endif
       for (; work.next(sg); ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        GSTAMP(t_issue);
         mbar_wait(&tempty[as], aph ^ 1);  // epilogues have drained this accumulator
         tc_fence_after();
+        GSTAMP(t_acc);
+#ifdef B200_GEMM_TIMING
+        ++n_seg; n_kb += sg.kb1 - sg.kb0;
+#endif
         const uint32_t tacc = tmem_base + as * C::ACC_STRIDE;
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          GSTAMP(t_issue);
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          GSTAMP(t_full);
           const uint32_t a_addr = smem_u32(sA + s * C::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
 #pragma unroll
@@ -465,22 +504,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         // accumulator complete -> epilogues of both CTAs
         if constexpr (PAIR) umma_commit_pair(&tfull[as], 0x3); else umma_commit(&tfull[as]);
       }
+#ifdef B200_GEMM_TIMING
+      GSTAMP(t_issue);
+      if (blockIdx.x == 10) printf("gemm mma thread: %d segs %d kb | total %lld | wait tempty %lld | wait full %lld | issue %lld\n",
+                                   n_seg, n_kb, clock64() - t_start, t_acc, t_full, t_issue);
+#endif
     }
   } else if (warp >= 4) {
     // ===================== epilogue (every CTA, its own 128 rows) =====================
+    griddep_wait();                 // the output buffer may still be in use by the previous kernel
     const int q = warp & 3;         // TMEM lane quadrant this warp may access
     const int g = (warp - 4) >> 2;  // column group
     const uint32_t stg = smem_u32(sStg) + (warp - 4) * C::STG_WARP;
     int it = 0;
-    WorkIter work(num_tiles, num_kb, unit, num_units, p.stream_k != 0);
+    WorkIter work(num_tiles, num_kb, unit, num_units, (p.stream_k & 1) != 0);
     Segment sg;
+#ifdef B200_GEMM_TIMING
+    long long e_wait = 0, e_busy = 0, e_prev = clock64(), e_start = e_prev;
+#define ESTAMP(v) do { long long _n = clock64(); v += _n - e_prev; e_prev = _n; } while (0)
+#else
+#define ESTAMP(v)
+#endif
     for (; work.next(sg); ++it) {
       const int m0 = (sg.tile / num_n) * MT + rank * BM;
       const int n0 = (sg.tile % num_n) * BN;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      ESTAMP(e_busy);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      ESTAMP(e_wait);
       const uint32_t taddr = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16) + g * CW;
       epilogue_tile<EPI, CW>(taddr, m0 + q * 32, lane, n0 + g * CW, p, &tma_out, stg, sg.kb0 == 0);
       tc_fence_before();
@@ -490,7 +543,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         else mbar_arrive(&tempty[as]);
       }
     }
+    ESTAMP(e_busy);
     if (epi_stage_bytes(EPI) > 0 && lane == 0) bulk_wait<0>();  // all TMA stores / reductions have landed
+#ifdef B200_GEMM_TIMING
+    if (blockIdx.x == 10 && warp == 4 && lane == 0) {
+      const long long tail = clock64() - e_prev;
+      printf("gemm epilogue warp: total %lld | wait tfull %lld | busy %lld | final bulk wait %lld\n", clock64() - e_start, e_wait, e_busy, tail);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -505,6 +565,15 @@ bool stream_k_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200VIT_STREAM_K");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+bool weight_prefetch_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VIT_BPREFETCH");
     v = (e == nullptr || e[0] != '0') ? 1 : 0;
   }
   return v == 1;
@@ -556,7 +625,7 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     g.valid = true;
   }
   GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const uint32_t*>(a.d_rope), a.m, a.n, a.k, a.ldo,
-               a.rope_cols, g.stream_k};
+               a.rope_cols, g.stream_k | (weight_prefetch_enabled() ? 0 : 2)};
   auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {

@@ -28,7 +28,7 @@ int check_arch();  // 0 if the current device is sm_100, else B200VIT_EARCH
 // out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
 // General 2-D row-major map: elem_bytes 2 (bf16) or 4 (fp32), row pitch `pitch_elems`, box = [box_rows, box_cols],
-// swizzle_bytes = 0 (none), 32 or 128 (box_cols * elem_bytes must equal the swizzle width).
+// swizzle_bytes = 0 (none), 32, 64 or 128 (box_cols * elem_bytes must equal the swizzle width).
 int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int elem_bytes,
                  int box_rows, int box_cols, int swizzle_bytes);
 

@@ -122,6 +122,11 @@ __device__ __forceinline__ uint32_t swz128(uint32_t base, int row, int j) {
   return base + row * 128 + ((j ^ (row & 7)) << 4);
 }
 
+// same for a [rows x 64 B] SWIZZLE_64B tile (512-aligned): 16-byte chunk index XOR ((row >> 1) & 3)
+__device__ __forceinline__ uint32_t swz64(uint32_t base, int row, int j) {
+  return base + row * 64 + ((j ^ ((row >> 1) & 3)) << 4);
+}
+
 // ---------------------------------------------------------------- clusters / CTA pairs
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
