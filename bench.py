@@ -218,6 +218,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BENCH_STREAMS", "1")),
+                    help="clips in flight per GPU (CUDA streams, one workspace each); measured: 2 is 2.7 % slower than 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -263,27 +265,43 @@ def main():
 
     pending = [None, None]
     step_no = [0]
+    n_streams = max(1, min(args.streams, 2))
+    main_stream = torch.cuda.current_stream(dev)
+    side = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else [main_stream]
 
     def step_resident():
-        """One clip through the path; with N > 1 the merged tokens go to rank 0 on NCCL's stream while the next
-        clip is already being computed (two output buffers; a buffer is reused only after its gather finished)."""
+        """One clip through the path.  Consecutive clips alternate between `n_streams` CUDA streams (one workspace
+        and one output buffer each), so one clip's kernel tails / set-up overlap the other clip's kernels; with
+        N > 1 the merged tokens go to rank 0 on NCCL's stream while the next clip is already being computed."""
         b = step_no[0] & 1
         step_no[0] += 1
-        if pending[b] is not None:
-            pending[b].wait()          # stream-level wait, the host does not block
-            pending[b] = None
-        tower.forward_frames(frames_dev, overlay, out=outs[b])
-        if do_gather:
-            if gmode == "gather":
-                pending[b] = dist.gather(outs[b], gather_lists[b], dst=0, async_op=True)
-            else:
-                gather_out(outs[b])
+        st = side[b % n_streams]
+        with torch.cuda.stream(st):
+            if pending[b] is not None:
+                pending[b].wait()          # stream-level wait, the host does not block
+                pending[b] = None
+            tower.forward_frames(frames_dev, overlay, out=outs[b], slot=b % n_streams)
+            if do_gather:
+                if gmode == "gather":
+                    pending[b] = dist.gather(outs[b], gather_lists[b], dst=0, async_op=True)
+                else:
+                    gather_out(outs[b])
+
+    def fork():
+        for st in side:
+            if st is not main_stream:
+                st.wait_stream(main_stream)
 
     def drain():
         for b in (0, 1):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
+            st = side[b % n_streams]
+            with torch.cuda.stream(st):
+                if pending[b] is not None:
+                    pending[b].wait()
+                    pending[b] = None
+        for st in side:
+            if st is not main_stream:
+                main_stream.wait_stream(st)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -292,10 +310,13 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- resident-input timing
+    fork()
     for _ in range(args.warmup - 1):
         step_resident()
+    drain()
     torch.cuda.synchronize(dev)
     t_w = time.perf_counter()
+    fork()
     step_resident()
     drain()
     torch.cuda.synchronize(dev)
@@ -309,6 +330,7 @@ def main():
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    fork()
     for _ in range(args.steps):
         step_resident()
     drain()
@@ -405,6 +427,7 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "weights": "random-init Qwen2.5-VL-7B vision tower shape (676.6M params)",
                        "parallelism": f"clip-sharded dp{world}, merged tokens gathered to rank 0" if world > 1 else "single GPU",
+                       "clips_in_flight_per_gpu": n_streams,
                        "l2": "per-step working set (1.35 GB bf16 weights + 0.3 GB activations) exceeds the 126 MB L2; no flush needed"},
             "tokens_per_s": fps * (m // 4) / T_FRAMES,
             "tower_tflops": total_flops * world / (step_ms * 1e-3) / 1e12,

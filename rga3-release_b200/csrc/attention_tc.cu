@@ -377,8 +377,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         tmem_ld32(ts + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
         if (__all_sync(0xffffffffu, c >= lo && c + 64 <= hi)) {
+          float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};  // independent chains: a single fmax chain is latency-bound
 #pragma unroll
-          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 64; i += 4) {
+            m4[0] = fmaxf(m4[0], __uint_as_float(v[i]));
+            m4[1] = fmaxf(m4[1], __uint_as_float(v[i + 1]));
+            m4[2] = fmaxf(m4[2], __uint_as_float(v[i + 2]));
+            m4[3] = fmaxf(m4[3], __uint_as_float(v[i + 3]));
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         } else {
 #pragma unroll
           for (int i = 0; i < 64; ++i) mx = fmaxf(mx, (c + i >= lo && c + i < hi) ? __uint_as_float(v[i]) : -INFINITY);
@@ -406,13 +413,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         tmem_ld_wait();
         uint32_t pk[16];
         if (__all_sync(0xffffffffu, c >= lo && c + 32 <= hi)) {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial sums (ILP)
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
+          for (int i = 0; i < 32; i += 4) {
             const float p0 = ex2_approx(__uint_as_float(v[i]) * scale_log2 - m_use);
             const float p1 = ex2_approx(__uint_as_float(v[i + 1]) * scale_log2 - m_use);
-            sum += p0 + p1;
+            const float p2 = ex2_approx(__uint_as_float(v[i + 2]) * scale_log2 - m_use);
+            const float p3 = ex2_approx(__uint_as_float(v[i + 3]) * scale_log2 - m_use);
+            s4[0] += p0, s4[1] += p1, s4[2] += p2, s4[3] += p3;
             pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
           }
+          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {

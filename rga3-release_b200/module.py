@@ -214,15 +214,18 @@ class B200VisionTower(nn.Module):
         return self._packed[0]
 
     # ---- plans
-    def plan_for(self, grid_thw) -> _Plan:
+    def plan_for(self, grid_thw, slot: int = 0) -> _Plan:
+        """Plan (index tables, workspace, launch memos) for this grid.  `slot` selects an independent instance so
+        several clips can be in flight on different CUDA streams (one workspace per slot)."""
         if isinstance(grid_thw, torch.Tensor):
             grid = tuple(tuple(int(v) for v in row) for row in grid_thw.detach().cpu().tolist())
         else:
             grid = tuple(tuple(int(v) for v in row) for row in np.asarray(grid_thw).reshape(-1, 3).tolist())
-        p = self._plans.get(grid)
+        key = (grid, int(slot))
+        p = self._plans.get(key)
         if p is None:
             p = _Plan(grid, self._cfg_c, self._device)
-            self._plans[grid] = p
+            self._plans[key] = p
         return p
 
     # ---- the hot path
@@ -303,7 +306,7 @@ class B200VisionTower(nn.Module):
 
     @torch.no_grad()
     def forward_frames(self, frames_u8: torch.Tensor, overlay: Optional[OverlaySpec] = None, grid_thw=None,
-                       out: Optional[torch.Tensor] = None):
+                       out: Optional[torch.Tensor] = None, slot: int = 0):
         """Fused entry: uint8 frames [T,H,W,3] (CUDA) + optional STOM overlay -> merged embeddings.
         Equivalent to PIL overlay -> Qwen2VLVideoProcessor(do_resize=False) -> tower."""
         if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
@@ -312,7 +315,7 @@ class B200VisionTower(nn.Module):
         if grid_thw is None:
             tps = self.temporal_patch_size
             grid_thw = [[(t + tps - 1) // tps, h // self.patch_size, w // self.patch_size]]
-        plan = self.plan_for(grid_thw)
+        plan = self.plan_for(grid_thw, slot)
         fr = frames_u8.contiguous()
         fc = _lib.Frames(fr.data_ptr(), t, h, w)
         oc = overlay.to_c(t) if overlay is not None else None
