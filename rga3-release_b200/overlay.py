@@ -109,6 +109,7 @@ class OverlaySpec:
             for j in range(4):
                 ops[i].rgba[j] = int(o.rgba[j])
         ov.h_ops = ops
+        ov._refs = (ops, self.layer)   # the C view keeps its backing storage alive, even if this spec is a temporary
         self._c_keep = (ov, ops)
         return ov
 

@@ -269,3 +269,72 @@ def test_patchify_golden_fixture(golden_dir):
     _lib.check(_lib.lib().b200vit_overlay_patchify(C.byref(fc), None, 14, 2, 2, out.data_ptr(), _stream()), "patchify")
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), torch.from_numpy(z["pixel_values"]).to(torch.bfloat16))
+
+
+def test_overlay_long_clip_multiple_launch_windows():
+    """More than 128 frames: the per-frame ops travel as kernel parameters in windows of 128 frames; odd T exercises
+    the repeat-last-frame padding across the window boundary."""
+    t, h, w = 131, 28, 56
+    frames = _clip(t, h, w, 52)
+    layer = _layer(h, w)
+    ops = [vit.FrameOp(mode=_lib.FRAME_LAYER, sx=(i % 7) - 3, sy=(i % 5) - 2) if i % 3 else vit.FrameOp() for i in range(t)]
+    ref_ops = [dict(mode=1, sx=(i % 7) - 3, sy=(i % 5) - 2) if i % 3 else dict(mode=0) for i in range(t)]
+    spec = vit.OverlaySpec.from_rgba(layer, ops)
+    fr = frames.to(DEV)
+    fc = _lib.Frames(fr.data_ptr(), t, h, w)
+    oc = spec.to_c(t)
+    comp = torch.zeros_like(fr)
+    _lib.check(_lib.lib().b200vit_overlay_composite(C.byref(fc), C.byref(oc), comp.data_ptr(), _stream()), "composite")
+    torch.cuda.synchronize()
+    ref = overlay_ref.overlay_clip_ref(frames.numpy(), layer, ref_ops)
+    assert np.array_equal(comp.cpu().numpy(), ref)
+    pv_ref, grid = patchify_ref.patchify_ref(ref)
+    assert grid.tolist() == [[66, 2, 4]]
+    out = torch.zeros(pv_ref.shape, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().b200vit_overlay_patchify(C.byref(fc), C.byref(oc), 14, 2, 2, out.data_ptr(), _stream()), "patchify")
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), torch.from_numpy(pv_ref).to(torch.bfloat16))
+
+
+def test_overlay_extreme_shifts_and_no_overlay():
+    t, h, w = 4, 56, 56
+    frames = _clip(t, h, w, 53)
+    layer = _layer(h, w)
+    shifts = [(0, 0), (w, 0), (-w - 3, 5), (17, -h + 1)]   # fully off-screen and partially visible layers
+    ops = [vit.FrameOp(mode=_lib.FRAME_LAYER, sx=sx, sy=sy) for sx, sy in shifts]
+    ref_ops = [dict(mode=1, sx=sx, sy=sy) for sx, sy in shifts]
+    fr = frames.to(DEV)
+    fc = _lib.Frames(fr.data_ptr(), t, h, w)
+    oc = vit.OverlaySpec.from_rgba(layer, ops).to_c(t)
+    comp = torch.zeros_like(fr)
+    _lib.check(_lib.lib().b200vit_overlay_composite(C.byref(fc), C.byref(oc), comp.data_ptr(), _stream()), "composite")
+    torch.cuda.synchronize()
+    assert np.array_equal(comp.cpu().numpy(), overlay_ref.overlay_clip_ref(frames.numpy(), layer, ref_ops))
+    # no overlay at all == plain processor output
+    pv_ref, _ = patchify_ref.patchify_ref(frames.numpy())
+    out = torch.zeros(pv_ref.shape, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().b200vit_overlay_patchify(C.byref(fc), None, 14, 2, 2, out.data_ptr(), _stream()), "patchify")
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), torch.from_numpy(pv_ref).to(torch.bfloat16))
+
+
+def test_overlay_rejects_bad_specs():
+    t, h, w = 2, 28, 28
+    fr = _clip(t, h, w, 54).to(DEV)
+    fc = _lib.Frames(fr.data_ptr(), t, h, w)
+    comp = torch.zeros_like(fr)
+    bad = vit.OverlaySpec(kind=_lib.LAYER_NONE, ops=[vit.FrameOp(mode=_lib.FRAME_LAYER)] * t)     # layer op without a layer
+    assert _lib.lib().b200vit_overlay_composite(C.byref(fc), C.byref(bad.to_c(t)), comp.data_ptr(), _stream()) == -1
+    bad2 = vit.OverlaySpec(kind=_lib.LAYER_NONE, ops=[vit.FrameOp(mode=_lib.FRAME_CIRCLE, r=500)] * t)   # radius too large
+    assert _lib.lib().b200vit_overlay_composite(C.byref(fc), C.byref(bad2.to_c(t)), comp.data_ptr(), _stream()) == -1
+    out = torch.zeros(4, 1176, dtype=torch.bfloat16, device=DEV)
+    fc_bad = _lib.Frames(fr.data_ptr(), t, 27, 28)                                                 # not a multiple of 28
+    assert _lib.lib().b200vit_overlay_patchify(C.byref(fc_bad), None, 14, 2, 2, out.data_ptr(), _stream()) == -1
+
+
+def test_cast_fp16_and_tail():
+    x = rnd((7, 1176), 41, 1.0, torch.float16)   # 8232 elements: not a multiple of the 8-wide vector path per thread block
+    out = torch.zeros(7, 1176, dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().b200vit_cast_to_bf16(x.data_ptr(), 1, out.data_ptr(), x.numel(), _stream()), "cast")
+    torch.cuda.synchronize()
+    assert torch.equal(out, x.to(torch.bfloat16))

@@ -239,3 +239,19 @@ def test_splice_into_inputs_embeds_in_place():
         vit.splice_span(torch.tensor([990, 1, 990]), 990)
     with pytest.raises(ValueError):
         t(x, torch.tensor(grid), out=emb[0, :length - 1])
+
+
+def test_forward_frames_odd_frame_count_and_fp32_pixels():
+    """Odd T (last frame repeated, HF videoproc :245-249) through the fused entry == oracle patchify -> tower; fp32 and
+    fp16 pixel_values take the cast kernel."""
+    t, cfg, sd = make_tower(hf_ref.CFG_SMALL, output_fp32=True)
+    frames = hf_ref.synthetic_frames(5, 56, 84, clip_id=7)
+    pv, grid = patchify_ref.patchify_ref(frames.numpy())
+    ref = tower_ref.tower_forward_ref(sd, cfg, torch.from_numpy(pv), grid)
+    out = t.forward_frames(frames.to(DEV))
+    cos, rel = parity(out, ref)
+    assert cos >= COS_MIN and rel <= REL_MAX, (cos, rel)
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        o2 = t(torch.from_numpy(pv).to(DEV).to(dt), torch.from_numpy(grid))
+        cos, rel = parity(o2, ref)
+        assert cos >= COS_MIN and rel <= REL_MAX, (dt, cos, rel)
