@@ -197,9 +197,16 @@ struct L2Persist {
       if (!(enabled && max_persist > 0)) enabled = 0;
       cudaGetLastError();
     }
-    if (!enabled || bytes == 0) return;
     static size_t set_aside = 0;  // carve out only what the residual stream needs: the rest stays normal L2
-    const size_t want = bytes < max_persist ? bytes : max_persist;
+    if (!enabled || bytes == 0) return;
+    if (bytes > max_persist || bytes > max_window) {
+      // long clips: the residual stream does not fit the persisting partition; a partial window only shrinks the
+      // normal L2 (measured on cfg 4) -- give the carve-out back and stream
+      if (set_aside != 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) == cudaSuccess) set_aside = 0;
+      cudaGetLastError();
+      return;
+    }
+    const size_t want = bytes;
     if (want != set_aside) {
       if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
         cudaGetLastError();
