@@ -21,6 +21,7 @@
 
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -37,6 +38,12 @@ constexpr int T64_BYTES = 128 * 128;  // [128 rows][64 cols] bf16
 constexpr int T16_BYTES = 128 * 32;   // [128 rows][16 cols] bf16
 constexpr int TILE_BYTES = T64_BYTES + T16_BYTES;
 constexpr int P_BYTES = 2 * T64_BYTES;  // [128][128] bf16 as two 64-wide K-major sub-tiles
+// V is the MN-major B operand of P.V.  Every tcgen05.mma of this shape costs >= 64 cycles whatever its N (the 4 KB A
+// operand is re-read from shared memory), so the 80 output columns must come from ONE N=80 instruction per k-step, not a
+// 64-wide plus a 16-wide one: the 16-column tail is therefore loaded as a second full 64-column SWIZZLE_128B atom
+// (columns 64..127 of the head; the 48 surplus columns belong to the next head or are zero-filled past the matrix edge
+// and are never read by the MMA), LBO = T64_BYTES apart.
+constexpr int V_TILE_BYTES = 2 * T64_BYTES;
 
 // SHARED_KV = true  (full layers): the QTILES query tiles are consecutive 128-row tiles of ONE head and share
 //                     each K/V block (NKV-deep ring); the CTA may walk several heads (NQ Q buffers).
@@ -50,7 +57,7 @@ struct AttnCfg {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQBUF * TILE_BYTES;
   static constexpr int OFF_V = OFF_K + NKBUF * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + NKBUF * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + NKBUF * V_TILE_BYTES;
   static constexpr int OFF_BAR = OFF_P + QTILES * P_BYTES;
   static constexpr int BYTES = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = QTILES == 2 ? 512 : 256;
@@ -74,9 +81,8 @@ constexpr uint64_t SW128 = 2, SW32 = 6;
 // K-major, 32-byte rows (16 bf16), SWIZZLE_32B: 8-row groups 256 B apart
 __device__ __forceinline__ uint64_t desc_k_sw32(uint32_t saddr) { return desc_common(saddr, 16, 256, SW32); }
 // MN-major B operand, rows = K index: 128-byte rows (64 bf16 of N), 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) { return desc_common(saddr, 1024, 1024, SW128); }
-// MN-major B operand, 32-byte rows (16 bf16 of N), 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t saddr) { return desc_common(saddr, 256, 256, SW32); }
+// and 64-column atoms T64_BYTES apart (canonical ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in elements)
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) { return desc_common(saddr, T64_BYTES, 1024, SW128); }
 
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
@@ -161,6 +167,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         tma_load_2d(dst, &tm64, bar, col, row);
         tma_load_2d(dst + T64_BYTES, &tm16, bar, col + 64, row);
       };
+      auto load_v = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+        tma_load_2d(dst, &tm64, bar, col, row);
+        tma_load_2d(dst + T64_BYTES, &tm64, bar, col + 64, row);
+      };
       if constexpr (SHARED_KV) {
         int i = 0;
         for (int hl = 0; hl < n_hl; ++hl) {
@@ -179,8 +189,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
             mbar_arrive_expect_tx(&k_full[b], TILE_BYTES);
             load_tile(smem + L::OFF_K + b * TILE_BYTES, &k_full[b], D + head * HD, row);
             mbar_wait(&v_empty[b], par);
-            mbar_arrive_expect_tx(&v_full[b], TILE_BYTES);
-            load_tile(smem + L::OFF_V + b * TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
+            mbar_arrive_expect_tx(&v_full[b], V_TILE_BYTES);
+            load_v(smem + L::OFF_V + b * V_TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
           }
         }
       } else {
@@ -201,8 +211,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
               mbar_arrive_expect_tx(&k_full[t], TILE_BYTES);
               load_tile(smem + L::OFF_K + t * TILE_BYTES, &k_full[t], D + head * HD, row);
               mbar_wait(&v_empty[t], par);
-              mbar_arrive_expect_tx(&v_full[t], TILE_BYTES);
-              load_tile(smem + L::OFF_V + t * TILE_BYTES, &v_full[t], 2 * D + head * HD, row);
+              mbar_arrive_expect_tx(&v_full[t], V_TILE_BYTES);
+              load_v(smem + L::OFF_V + t * V_TILE_BYTES, &v_full[t], 2 * D + head * HD, row);
             }
       }
     }
@@ -210,8 +220,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = idesc_bf16(QT, KVB, false);
-      constexpr uint32_t idesc_pv64 = idesc_bf16(QT, 64, true);
-      constexpr uint32_t idesc_pv16 = idesc_bf16(QT, 16, true);
+      constexpr uint32_t idesc_pv = idesc_bf16(QT, HD, true);
       auto kv_stage = [&](int t, int i) { return SHARED_KV ? (i % NKV) : t; };
       auto q_slot = [&](int t, int i) { return SHARED_KV ? (((i / nblk) % NQ) * QTILES + t) : t; };
       auto issue_qk = [&](int t, int i) {  // S(t) is free: the caller has waited p_full(t, i-1)
@@ -229,13 +238,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         mbar_wait(&o_empty[t], (i & 1) ^ 1);  // accumulate(t, i-1) has drained O(t)
         tc_fence_after();
         const uint32_t p0 = smem_u32(smem + L::OFF_P + t * P_BYTES);
-        const uint32_t v64 = smem_u32(smem + L::OFF_V + kv_stage(t, i) * TILE_BYTES), v16 = v64 + T64_BYTES;
+        const uint32_t v64 = smem_u32(smem + L::OFF_V + kv_stage(t, i) * V_TILE_BYTES);
         const uint32_t to = tmem_base + L::O_COL(t);
 #pragma unroll
         for (int k = 0; k < KVB / 16; ++k) {
           const uint64_t pa = umma_desc_k128(p0 + (k >> 2) * T64_BYTES + (k & 3) * 32);
-          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv64, k != 0 ? 1u : 0u);
-          umma_bf16_ss(to + 64, pa, desc_mn_sw32(v16 + k * 512), idesc_pv16, k != 0 ? 1u : 0u);
+          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv, k != 0 ? 1u : 0u);
         }
         umma_commit(&o_full[t]);
       };
@@ -496,6 +504,401 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------ full-attention layers, two threads per row
+// Same pipeline as attn_tc_kernel<2, 2, 1, true> (two 128-row query tiles of one head sharing each K/V block), but the
+// softmax is issue/latency-bound with one thread per row (phase timings: 3.1 k cycles per block and tile), so every row is
+// split between TWO threads (64 score columns / 40 output columns each; 16 softmax warps instead of 8).  The partners
+// exchange their partial row maximum through shared memory once per block and their partial row sums once at the end.
+constexpr int F2_THREADS = 64 + 512;
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
+                  const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap to16,
+                  const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, int m_rows, int heads,
+                  float scale_log2) {
+  using L = AttnCfg<2, 2, 1, true>;
+  constexpr int NKV = 2;
+  griddep_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + NKV;
+  uint64_t* v_full = k_empty + NKV;
+  uint64_t* v_empty = v_full + NKV;
+  uint64_t* s_full = v_empty + NKV;  // [2]
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 2;
+  uint64_t* o_empty = o_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  float* exch = reinterpret_cast<float*>(smem + L::OFF_BAR + 256);  // [2 parities][2 tiles][2 halves][128] floats = 4 KB
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AttnTile tile = tiles[blockIdx.x];
+  const int head = blockIdx.y;
+  const int D = heads * HD;
+  const int nblk = tile.n_kv_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm64);
+    tma_prefetch_desc(&tm16);
+    tma_prefetch_desc(&to64);
+    tma_prefetch_desc(&to16);
+    mbar_init(q_full, 1);
+    for (int b = 0; b < NKV; ++b) {
+      mbar_init(&k_full[b], 1);
+      mbar_init(&k_empty[b], 1);
+      mbar_init(&v_full[b], 1);
+      mbar_init(&v_empty[b], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 256);
+      mbar_init(&o_full[t], 1);
+      mbar_init(&o_empty[t], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+        tma_load_2d(dst, &tm64, bar, col, row);
+        tma_load_2d(dst + T64_BYTES, &tm16, bar, col + 64, row);
+      };
+      auto load_v = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+        tma_load_2d(dst, &tm64, bar, col, row);
+        tma_load_2d(dst + T64_BYTES, &tm64, bar, col + 64, row);
+      };
+      mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+      for (int t = 0; t < 2; ++t) load_tile(smem + L::OFF_Q + t * TILE_BYTES, q_full, head * HD, tile.q_row0 + t * QT);
+      for (int j = 0; j < nblk; ++j) {
+        const int b = j % NKV;
+        const uint32_t par = ((j / NKV) & 1) ^ 1;
+        const int row = tile.kv_row0 + j * KVB;
+        mbar_wait(&k_empty[b], par);
+        mbar_arrive_expect_tx(&k_full[b], TILE_BYTES);
+        load_tile(smem + L::OFF_K + b * TILE_BYTES, &k_full[b], D + head * HD, row);
+        mbar_wait(&v_empty[b], par);
+        mbar_arrive_expect_tx(&v_full[b], V_TILE_BYTES);
+        load_v(smem + L::OFF_V + b * V_TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = idesc_bf16(QT, KVB, false);
+      constexpr uint32_t idesc_pv = idesc_bf16(QT, HD, true);
+      auto issue_qk = [&](int t, int i) {
+        const uint32_t q64 = smem_u32(smem + L::OFF_Q + t * TILE_BYTES), q16 = q64 + T64_BYTES;
+        const uint32_t k64 = smem_u32(smem + L::OFF_K + (i % NKV) * TILE_BYTES), k16 = k64 + T64_BYTES;
+        const uint32_t ts = tmem_base + L::S_COL(t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(ts, umma_desc_k128(q64 + k * 32), umma_desc_k128(k64 + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+        umma_bf16_ss(ts, desc_k_sw32(q16), desc_k_sw32(k16), idesc_qk, 1u);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int i) {
+        mbar_wait(&p_full[t], i & 1);
+        mbar_wait(&o_empty[t], (i & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t p0 = smem_u32(smem + L::OFF_P + t * P_BYTES);
+        const uint32_t v64 = smem_u32(smem + L::OFF_V + (i % NKV) * V_TILE_BYTES);
+        const uint32_t to = tmem_base + L::O_COL(t);
+#pragma unroll
+        for (int k = 0; k < KVB / 16; ++k) {
+          const uint64_t pa = umma_desc_k128(p0 + (k >> 2) * T64_BYTES + (k & 3) * 32);
+          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[t]);
+      };
+#ifdef B200_ATTN_TIMING
+      long long mt[4] = {0, 0, 0, 0};
+      long long mprev = clock64();
+#define MSTAMP(k) do { long long _n = clock64(); mt[k] += _n - mprev; mprev = _n; } while (0)
+#else
+#define MSTAMP(k)
+#endif
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      MSTAMP(0);
+      for (int t = 0; t < 2; ++t) issue_qk(t, 0);
+      umma_commit(&k_empty[0]);
+#ifdef B200_ATTN_MMA_SERIAL
+      // measurement only: run every MMA group to completion before issuing the next one and time it
+      for (int i = 0; i < nblk; ++i) {
+        const int b = i % NKV;
+        mbar_wait(&v_full[b], (i / NKV) & 1);
+        const bool more = i + 1 < nblk;
+        if (more) mbar_wait(&k_full[(i + 1) % NKV], ((i + 1) / NKV) & 1);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], i & 1);
+          mbar_wait(&o_empty[t], (i & 1) ^ 1);
+          long long c0 = clock64();
+          issue_pv(t, i);
+          mbar_wait(&o_full[t], i & 1);
+          long long c1 = clock64();
+          if (more) {
+            issue_qk(t, i + 1);
+            mbar_wait(&s_full[t], (i + 1) & 1);
+          }
+          long long c2 = clock64();
+          mt[3] += c1 - c0;
+          if (more) mt[2] += c2 - c1;
+        }
+        umma_commit(&v_empty[b]);
+        if (more) umma_commit(&k_empty[(i + 1) % NKV]);
+      }
+      if (blockIdx.x == 1 && blockIdx.y == 0) printf("full2 serial mma: pv total %lld (%d groups) | qk total %lld (%d groups)\n", mt[3], 2 * nblk, mt[2], 2 * (nblk - 1));
+#else
+      // The two tiles advance independently (whichever tile's softmax has delivered P is served, so one tile's softmax
+      // overlaps the other tile's tensor-core work), and inside a tile the NEXT Q.K^T goes ahead of the current P.V:
+      // S(t) is free as soon as softmax(i) has read it, so S(i+1) is produced while the softmax warps still fold
+      // O(i-1) into their registers; P.V(i) follows when they have drained O(t).  The softmax warps wait for P.V(i)
+      // before they overwrite P (see below).  A K/V stage is released by the LATER of the two tiles.
+      int qk_done[2] = {1, 1}, pv_done[2] = {0, 0};
+      const long long t_start = clock64();
+      while (pv_done[0] < nblk || pv_done[1] < nblk) {
+        bool progressed = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          int i = qk_done[t];
+          if (i < nblk && mbar_test(&p_full[t], (i - 1) & 1) && mbar_test(&k_full[i % NKV], (i / NKV) & 1)) {
+            tc_fence_after();
+            issue_qk(t, i);
+            qk_done[t] = i + 1;
+            if (qk_done[t ^ 1] > i) umma_commit(&k_empty[i % NKV]);
+            progressed = true;
+          }
+          i = pv_done[t];
+          if (i < nblk && (qk_done[t] > i + 1 || i + 1 >= nblk) && mbar_test(&p_full[t], i & 1) &&
+              mbar_test(&o_empty[t], (i & 1) ^ 1) && mbar_test(&v_full[i % NKV], (i / NKV) & 1)) {
+            issue_pv(t, i);  // its own waits succeed immediately
+            pv_done[t] = i + 1;
+            if (pv_done[t ^ 1] > i) umma_commit(&v_empty[i % NKV]);
+            progressed = true;
+          }
+        }
+        if (!progressed) {
+          __nanosleep(40);
+          if (clock64() - t_start > 8000000000ll) {
+            printf("b200vit: attention scheduler timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
+            __trap();
+          }
+        }
+      }
+#endif
+#ifdef B200_ATTN_TIMING
+      MSTAMP(1);
+      if (blockIdx.x == 1 && blockIdx.y == 0) printf("full2 mma thread: first loads %lld | scheduling loop %lld\n", mt[0], mt[1]);
+#endif
+    }
+  } else {
+    // ===================== softmax + accumulation: two threads per query row =====================
+    const int sw = warp - 2;
+    const int t = sw >> 3;          // query tile
+    const int half = (sw >> 2) & 1; // score columns [64*half, +64), output columns [40*half, +40)
+    const int quad = warp & 3;      // TMEM lane quadrant
+    const int r = quad * 32 + lane;
+    const int row = tile.q_row0 + t * QT + r;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t ts = lane_base + L::S_COL(t) + half * 64;
+    const uint32_t to = lane_base + L::O_COL(t) + half * 40;
+    const uint32_t psub = smem_u32(smem + L::OFF_P + t * P_BYTES) + half * T64_BYTES;  // this half's 64-wide P sub-tile
+    const int bar_id = 1 + t;
+    int2 bd = make_int2(0, 0);
+    if (row < m_rows) bd = bounds[row];
+    float o[40];
+#pragma unroll
+    for (int i = 0; i < 40; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_part = 0.f, alpha_prev = 1.f;
+#ifdef B200_ATTN_TIMING
+    long long tstamp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+    const bool trec = (blockIdx.x == 1 && blockIdx.y == 0 && (warp == 2 || warp == 14) && lane == 0);
+#define TSTAMP2(k) do { long long _n = clock64(); tstamp[k] += _n - tprev; tprev = _n; } while (0)
+#else
+#define TSTAMP2(k)
+#endif
+
+    auto accumulate_block = [&](int i, float alpha) {
+      mbar_wait(&o_full[t], i & 1);
+      tc_fence_after();
+      uint32_t v[32], v8[8];
+      tmem_ld32(to, v);
+      tmem_ld8(to + 32, v8);
+      tmem_ld_wait();
+      const uint64_t al2 = f32x2_pack(alpha, alpha);
+#pragma unroll
+      for (int i2 = 0; i2 < 32; i2 += 2)
+        f32x2_unpack(f32x2_fma(f32x2_pack(o[i2], o[i2 + 1]), al2, f32x2_pack_bits(v[i2], v[i2 + 1])), o[i2], o[i2 + 1]);
+#pragma unroll
+      for (int i2 = 0; i2 < 8; i2 += 2)
+        f32x2_unpack(f32x2_fma(f32x2_pack(o[32 + i2], o[33 + i2]), al2, f32x2_pack_bits(v8[i2], v8[i2 + 1])), o[32 + i2],
+                     o[33 + i2]);
+      tc_fence_before();
+      mbar_arrive(&o_empty[t]);
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      TSTAMP2(0);
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      TSTAMP2(1);
+      const int kv0 = tile.kv_row0 + j * KVB + half * 64;            // first kv row of this thread's column half
+      const int lo = max(bd.x - kv0, 0), hi = min(bd.y - kv0, 64);   // valid columns inside the half
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        if (__all_sync(0xffffffffu, c + 32 <= lo || c >= hi)) continue;
+        uint32_t v[32];
+        TSTAMP2(2);
+        tmem_ld32(ts + c, v);
+        tmem_ld_wait();
+        TSTAMP2(9);
+        if (__all_sync(0xffffffffu, c >= lo && c + 32 <= hi)) {
+          float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            m4[0] = fmaxf(m4[0], __uint_as_float(v[i]));
+            m4[1] = fmaxf(m4[1], __uint_as_float(v[i + 1]));
+            m4[2] = fmaxf(m4[2], __uint_as_float(v[i + 2]));
+            m4[3] = fmaxf(m4[3], __uint_as_float(v[i + 3]));
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i >= lo && c + i < hi) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      }
+      // partner exchange of the partial row maximum (double-buffered by block parity)
+      float* ex = exch + ((j & 1) * 2 + t) * 256;
+      TSTAMP2(2);
+      ex[half * 128 + r] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(mx, ex[(half ^ 1) * 128 + r]);
+      TSTAMP2(3);
+      const float m_new = fmaxf(m_run, mx * scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2_approx(m_run - m_use);
+      float sum = 0.f;
+      if (j >= 1) mbar_wait(&o_full[t], (j - 1) & 1);  // P.V(j-1) has finished reading P before it is overwritten
+      TSTAMP2(7);
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        const int j0 = c >> 3;
+        if (__all_sync(0xffffffffu, c + 32 <= lo || c >= hi)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st_shared_v4(swz128(psub, r, j0 + q), 0u, 0u, 0u, 0u);
+          continue;
+        }
+        uint32_t v[32];
+        TSTAMP2(4);
+        tmem_ld32(ts + c, v);
+        tmem_ld_wait();
+        TSTAMP2(8);
+        uint32_t pk[16];
+        if (__all_sync(0xffffffffu, c >= lo && c + 32 <= hi)) {
+          // packed fp32x2 FFMA / FADD: the softmax is issue-bound (ncu: 0.48 IPC with 3.4 k instructions per block and
+          // sub-partition), so two lanes per issue slot for everything except the MUFU itself
+          const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), nm2 = f32x2_pack(-m_use, -m_use);
+          uint64_t s2a = 0ull, s2b = 0ull;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float x0, x1, x2, x3;
+            f32x2_unpack(f32x2_fma(f32x2_pack_bits(v[i], v[i + 1]), sc2, nm2), x0, x1);
+            f32x2_unpack(f32x2_fma(f32x2_pack_bits(v[i + 2], v[i + 3]), sc2, nm2), x2, x3);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+            s2a = f32x2_add(s2a, f32x2_pack(p0, p1));
+            s2b = f32x2_add(s2b, f32x2_pack(p2, p3));
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
+          float sa, sb, sc, sd;
+          f32x2_unpack(s2a, sa, sb);
+          f32x2_unpack(s2b, sc, sd);
+          sum += (sa + sb) + (sc + sd);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(__uint_as_float(v[i]) * scale_log2 - m_use);
+            float p1 = ex2_approx(__uint_as_float(v[i + 1]) * scale_log2 - m_use);
+            p0 = (c + i >= lo && c + i < hi) ? p0 : 0.f;
+            p1 = (c + i + 1 >= lo && c + i + 1 < hi) ? p1 : 0.f;
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st_shared_v4(swz128(psub, r, j0 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+      l_part = l_part * alpha + sum;
+      m_run = m_new;
+      TSTAMP2(4);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+      TSTAMP2(5);
+      if (j >= 1) accumulate_block(j - 1, alpha_prev);
+      TSTAMP2(6);
+      alpha_prev = alpha;
+    }
+    accumulate_block(nblk - 1, alpha_prev);
+    TSTAMP2(6);
+
+    // combine the partners' partial row sums, then stage O (bf16) in this warp's own rows of the idle P buffer
+    float* ex = exch + ((nblk & 1) * 2 + t) * 256;
+    ex[half * 128 + r] = l_part;
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    const float l = l_part + ex[(half ^ 1) * 128 + r];
+    const float inv = (l > 0.f) ? 1.f / l : 0.f;
+    const uint32_t pbuf = smem_u32(smem + L::OFF_P + t * P_BYTES);
+    const uint32_t stg64 = pbuf + quad * 4096;              // [32 rows x 64 cols], SWIZZLE_128B
+    const uint32_t stg16 = pbuf + T64_BYTES + quad * 4096;  // [32 rows x 16 cols], dense
+#pragma unroll
+    for (int c = 0; c < 40; c += 8) {
+      const int col = half * 40 + c;  // output column of o[c]
+      const uint32_t w0 = pack_bf16x2(o[c] * inv, o[c + 1] * inv), w1 = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+      const uint32_t w2 = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), w3 = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+      if (col < 64) st_shared_v4(swz128(stg64, lane, col >> 3), w0, w1, w2, w3);
+      else st_shared_v4(stg16 + lane * 32 + (col - 64) * 2, w0, w1, w2, w3);
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");  // both halves of every row are staged
+    if (half == 0 && lane == 0) {
+      const int row0 = tile.q_row0 + t * QT + quad * 32;
+      tma_store_2d(&to64, stg64, head * HD, row0);
+      tma_store_2d(&to16, stg16, head * HD + 64, row0);
+      bulk_commit();
+      bulk_wait<0>();
+    }
+#ifdef B200_ATTN_TIMING
+    TSTAMP2(0);
+    if (trec) printf("full2 softmax warp %d (%d blocks): other+store %lld | wait_s %lld | pass1 %lld | exch %lld | wait_pv %lld | pass2 %lld | fence+arrive %lld | acc %lld | p1 ld %lld | p2 ld %lld\n",
+                     warp, nblk, tstamp[0], tstamp[1], tstamp[2], tstamp[3], tstamp[7], tstamp[4], tstamp[5], tstamp[6], tstamp[9], tstamp[8]);
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <int QTILES, int NKV, int NQ, bool SHARED_KV>
 int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, const int2* bd, int m_rows, int heads, int hpc,
                    float scale_log2, cudaStream_t stream) {
@@ -556,8 +959,24 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int2* bd = reinterpret_cast<const int2*>(d_bounds);
-  if (rows_per_tile == 256)
-    return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
+  if (rows_per_tile == 256) {
+    static int two_threads = -1;
+    if (two_threads < 0) {
+      const char* e = getenv("B200VIT_ATTN_FULL2");
+      two_threads = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    if (!two_threads) return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
+    using L = AttnCfg<2, 2, 1, true>;
+    constexpr int kSmem = L::BYTES + 4096;  // + partner-exchange area behind the barriers
+    static bool attr = false;
+    if (!attr) {
+      B200_CUDA_OK(cudaFuncSetAttribute(attn_full2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      attr = true;
+    }
+    B200_CUDA_OK(launch_kernel(attn_full2_kernel, dim3(n_tiles, heads), dim3(F2_THREADS), kSmem, stream, 1, g.tm64, g.tm16, g.to64,
+                               g.to16, d_tiles, bd, m_rows, heads, scale_log2));
+    return 0;
+  }
   if (rows_per_tile != 128) return fail(B200VIT_EINVAL, "attention: rows_per_tile must be 128 or 256");
   (void)max_blocks;
   if (heads % 2 != 0)  // odd head count: single stream, K/V double-buffered
