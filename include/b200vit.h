@@ -131,6 +131,9 @@ typedef struct b200vit_overlay {
   int32_t box[4];               /* BOX: l,t,r,b inclusive (PIL rectangle)              */
   int32_t box_width;
   const b200vit_frame_op* h_ops; /* HOST array [T]; circle stamps of one clip share r   */
+  const b200vit_frame_op* d_ops; /* DEVICE array [T] (e.g. written by b200vit_stom_policy); used when h_ops is
+                                    NULL.  Not validated by the host: an inconsistent op leaves its frame untouched */
+  int32_t d_ops_circle_r;        /* radius of the circle stamps in d_ops (min(h,w)/20, STOM.py:196), or -1        */
 } b200vit_overlay;
 
 typedef struct b200vit_frames {
@@ -169,6 +172,23 @@ int b200vit_profile_read(b200vit_plan* plan, float* h_ms_by_kind, int32_t* h_cou
 /* Overlay only: composited uint8 frames [T,H,W,3] (bit-exact vs PIL).         */
 int b200vit_overlay_composite(const b200vit_frames* frames, const b200vit_overlay* overlay, uint8_t* d_out,
                               b200vit_stream stream);
+/* STOM placement policy on the device (model/STOM.py:72-141 after the tracker): from tracker outputs
+ * d_tracks fp32 [T,N,2] (x,y) and d_vis u8 [T,N] (non-zero = visible) to one frame op per frame in d_ops
+ * (DEVICE array [T], the d_ops of b200vit_overlay), without a host round trip:
+ *   key frame            -> FRAME_LAYER, no shift (:82-86)
+ *   mask_shape == 0      -> MAD-filtered mean flow of the visible tracks (:104-131, numpy float32 semantics
+ *                           reproduced bit for bit), reduced to the integer shift of STOM.warp (:145-155);
+ *                           FRAME_NONE where the reference keeps the frame (:108-110, :122-124, :129-131)
+ *   mask_shape != 0      -> STOM.warp_point (:163-203): visible-track mask, closing with the k = min(h,w)/15
+ *                           ellipse, centroid, circle of radius min(h,w)/20 in the layer's first non-transparent
+ *                           colour with alpha clamped to [96,148]; FRAME_NONE where it returns/raises early
+ * d_layer_rgba: the RGBA prompt layer [h,w,4] (only read for mask shapes).  Workspace: b200vit_stom_policy_workspace_bytes.
+ * n_points <= 16384.                                                                                        */
+size_t b200vit_stom_policy_workspace_bytes(int32_t t_frames, int32_t n_points, int32_t h, int32_t w);
+int b200vit_stom_policy(const float* d_tracks, const uint8_t* d_vis, int32_t t_frames, int32_t n_points, int32_t key_idx,
+                        int32_t mask_shape, int32_t h, int32_t w, const uint8_t* d_layer_rgba, b200vit_frame_op* d_ops,
+                        void* d_workspace, size_t workspace_bytes, b200vit_stream stream);
+
 /* Overlay + normalise + patchify: bf16 [M, 3*tp*14*14] in processor order.    */
 int b200vit_overlay_patchify(const b200vit_frames* frames, const b200vit_overlay* overlay, int patch, int tps,
                              int merge, void* d_out_bf16, b200vit_stream stream);

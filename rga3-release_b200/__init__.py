@@ -6,7 +6,8 @@ from . import _lib
 from ._lib import B200VitError, lib
 from .module import B200VisionTower, install, splice_span
 from .dist import gather_tokens, shard_clips, shard_slices
-from .overlay import FrameOp, OverlaySpec, shift_from_flow, stom_frame_ops
+from .overlay import (FrameOp, OverlaySpec, frame_ops_from_bytes, shift_from_flow, stom_frame_ops,
+                      stom_frame_ops_device)
 
-__all__ = ["B200VisionTower", "install", "splice_span", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "lib", "shard_clips", "shard_slices", "gather_tokens",
+__all__ = ["B200VisionTower", "install", "splice_span", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "stom_frame_ops_device", "frame_ops_from_bytes", "lib", "shard_clips", "shard_slices", "gather_tokens",
            "B200VitError"]

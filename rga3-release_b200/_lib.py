@@ -44,7 +44,8 @@ class FrameOp(C.Structure):
 
 class Overlay(C.Structure):
     _fields_ = [("kind", C.c_int32), ("d_layer", C.c_void_p), ("palette", (C.c_uint8 * 4) * 256),
-                ("box", C.c_int32 * 4), ("box_width", C.c_int32), ("h_ops", C.POINTER(FrameOp))]
+                ("box", C.c_int32 * 4), ("box_width", C.c_int32), ("h_ops", C.POINTER(FrameOp)),
+                ("d_ops", C.c_void_p), ("d_ops_circle_r", C.c_int32)]
 
 
 class Frames(C.Structure):
@@ -73,6 +74,9 @@ EXPORTS = {
     "b200vit_overlay_composite": (C.c_int, [C.POINTER(Frames), C.POINTER(Overlay), C.c_void_p, C.c_void_p]),
     "b200vit_overlay_patchify": (C.c_int, [C.POINTER(Frames), C.POINTER(Overlay), C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p]),
+    "b200vit_stom_policy_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "b200vit_stom_policy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200vit_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200vit_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "b200vit_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p]),

@@ -39,6 +39,7 @@ struct OverlayParams {
   int32_t circle_r;
   uint32_t palette[256];
   int16_t circle_hw[256];
+  const b200vit_frame_op* d_ops;  // device-resident ops of this launch window (b200vit_stom_policy), or nullptr
   FrameOpDev ops[MAX_FRAMES_PER_LAUNCH];
 };
 
@@ -74,6 +75,23 @@ __device__ __forceinline__ uint32_t layer_at(const OverlayParams& ov, int h, int
     return (rows || cols) ? ov.palette[1] : 0u;
   }
   return 0u;
+}
+
+// Frame op `rel` of this launch window: from the kernel parameters (host ops, validated by fill_overlay) or from
+// device memory (written by b200vit_stom_policy; nothing the host could check, so anything inconsistent
+// degrades to "frame untouched").
+__device__ __forceinline__ FrameOpDev frame_op_at(const OverlayParams& ov, int rel) {
+  if (ov.d_ops == nullptr) return ov.ops[rel];
+  const int32_t* s = reinterpret_cast<const int32_t*>(ov.d_ops + rel);
+  FrameOpDev d;
+  d.mode = __ldg(s), d.sx = __ldg(s + 1), d.sy = __ldg(s + 2);
+  d.zx = __ldg(s + 3) ? 1 : 0, d.zy = __ldg(s + 4) ? 1 : 0, d.pad0 = d.pad1 = 0;
+  d.cx = __ldg(s + 5), d.cy = __ldg(s + 6), d.r = __ldg(s + 7);
+  d.rgba = static_cast<uint32_t>(__ldg(s + 8));  // bytes r,g,b,a little-endian
+  const bool ok = (d.mode == B200VIT_FRAME_LAYER && ov.kind != B200VIT_LAYER_NONE) ||
+                  (d.mode == B200VIT_FRAME_CIRCLE && d.r == ov.circle_r && d.r >= 0);
+  if (!ok) d.mode = B200VIT_FRAME_NONE;
+  return d;
 }
 
 // RGBA of the prompt layer as seen by destination pixel (y, x) of a frame; alpha 0 = untouched.
@@ -146,7 +164,7 @@ overlay_patchify_kernel(const __grid_constant__ PatchParams p, const __grid_cons
     const int y = y0 + ph, x = x0 + pw;
     uint32_t d = __ldg(p.frames + ((static_cast<size_t>(f - p.frame_base) * p.h + y) * p.w + x) * 3 + c);
     if (HAS_OVERLAY) {
-      const uint32_t s = overlay_at(ov, ov.ops[f - p.frame_base], p.h, p.w, y, x);
+      const uint32_t s = overlay_at(ov, frame_op_at(ov, f - p.frame_base), p.h, p.w, y, x);
       const uint32_t a = s >> 24;
       if (a) d = composite_ch(d, (s >> (8 * c)) & 0xffu, a);
     }
@@ -187,6 +205,11 @@ overlay_patchify_strip_kernel(const __grid_constant__ PatchParams p, const __gri
   constexpr int RH = SP * SMG;          // 28 pixel rows per strip
   const int rw = groups * RH;           // pixel columns of this block
   const int npx = STPS * RH * rw;
+  FrameOpDev fop[STPS];  // the ops of this block's STPS frames
+  if (HAS_OVERLAY) {
+#pragma unroll
+    for (int tp = 0; tp < STPS; ++tp) fop[tp] = frame_op_at(ov, min(tt * STPS + tp, p.t_total - 1) - p.frame_base);
+  }
 #pragma unroll 4
   for (int idx = threadIdx.x; idx < npx; idx += blockDim.x) {
     const int tp = idx / (RH * rw);
@@ -197,7 +220,7 @@ overlay_patchify_strip_kernel(const __grid_constant__ PatchParams p, const __gri
     const uint8_t* px = p.frames + ((static_cast<size_t>(f - p.frame_base) * p.h + y) * p.w + x) * 3;
     uint32_t d0 = __ldg(px), d1 = __ldg(px + 1), d2 = __ldg(px + 2);
     if (HAS_OVERLAY) {
-      const uint32_t sv = overlay_at(ov, ov.ops[f - p.frame_base], p.h, p.w, y, x);
+      const uint32_t sv = overlay_at(ov, fop[tp], p.h, p.w, y, x);
       const uint32_t a = sv >> 24;
       if (a) {
         d0 = composite_ch(d0, sv & 0xffu, a);
@@ -230,7 +253,7 @@ overlay_composite_kernel(const __grid_constant__ PatchParams p, const __grid_con
   const int x = static_cast<int>(gid % p.w);
   const int y = static_cast<int>((gid / p.w) % p.h);
   const int f = static_cast<int>(gid / (static_cast<int64_t>(p.w) * p.h));
-  const uint32_t s = overlay_at(ov, ov.ops[f], p.h, p.w, y, x);
+  const uint32_t s = overlay_at(ov, frame_op_at(ov, f), p.h, p.w, y, x);
   const uint32_t a = s >> 24;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -305,6 +328,15 @@ int fill_overlay(OverlayParams& o, const b200vit_overlay* ov, int f0, int nf, in
     o.palette[i] = ov->palette[i][0] | (ov->palette[i][1] << 8) | (ov->palette[i][2] << 16) |
                    (static_cast<uint32_t>(ov->palette[i][3]) << 24);
   o.circle_r = -1;
+  if (ov->h_ops == nullptr && ov->d_ops != nullptr) {
+    // device-resident ops: the kernels read (and sanity-check) them; only the shared circle radius is host knowledge
+    if (ov->d_ops_circle_r > 127) return fail(B200VIT_EINVAL, "overlay: circle radius must be in [0,127]");
+    if (reinterpret_cast<uintptr_t>(ov->d_ops) & 3) return fail(B200VIT_EALIGN, "overlay: d_ops must be 4-byte aligned");
+    o.d_ops = ov->d_ops + f0;
+    o.circle_r = ov->d_ops_circle_r >= 0 ? ov->d_ops_circle_r : -1;
+    if (o.circle_r >= 0) circle_halfwidths(o.circle_r, o.circle_hw);
+    return 0;
+  }
   for (int i = 0; i < nf; ++i) {
     FrameOpDev& d = o.ops[i];
     if (ov->h_ops == nullptr || f0 + i >= t_total) {
@@ -364,7 +396,7 @@ int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov,
       const int64_t threads = p.rows * (cols / 8);
       const int grid = static_cast<int>((threads + 255) / 256);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_bf16) + p.row_base * cols;
-      const bool has_ov = ov != nullptr && ov->h_ops != nullptr;
+      const bool has_ov = ov != nullptr && (ov->h_ops != nullptr || ov->d_ops != nullptr);
       if (patch == SP && tps == STPS && merge == SMG) {
         static bool attr_set = false;
         if (!attr_set) {

@@ -55,6 +55,9 @@ def shift_from_flow(flow: float, n: int) -> Tuple[int, int]:
     return shift, zero_extra
 
 
+FRAME_OP_BYTES = C.sizeof(_lib.FrameOp)  # 36
+
+
 @dataclass
 class OverlaySpec:
     """Prompt layer + per-frame ops.  ``layer`` is a CUDA uint8 tensor:
@@ -65,6 +68,10 @@ class OverlaySpec:
     box: Tuple[int, int, int, int] = (0, 0, 0, 0)
     box_width: int = 1
     ops: List[FrameOp] = field(default_factory=list)
+    # device-resident ops (``stom_frame_ops_device``): uint8 CUDA tensor [T, 36] holding b200vit_frame_op records;
+    # used instead of ``ops`` when set, so nothing about the placement ever visits the host
+    device_ops: Optional[torch.Tensor] = None
+    device_ops_circle_r: int = -1
 
     # ---- constructors mirroring image_blending's shapes
     @classmethod
@@ -101,6 +108,16 @@ class OverlaySpec:
         for i in range(4):
             ov.box[i] = int(self.box[i])
         ov.box_width = int(self.box_width)
+        if self.device_ops is not None:
+            d = self.device_ops
+            if not (d.is_cuda and d.dtype == torch.uint8 and d.is_contiguous() and d.numel() >= n_frames * FRAME_OP_BYTES):
+                raise ValueError("device_ops must be a contiguous CUDA uint8 tensor of at least [T, 36] bytes")
+            ov.h_ops = None
+            ov.d_ops = d.data_ptr()
+            ov.d_ops_circle_r = int(self.device_ops_circle_r)
+            ov._refs = (d, self.layer)
+            self._c_keep = (ov, d)
+            return ov
         ops = (_lib.FrameOp * n_frames)()
         for i in range(n_frames):
             o = self.ops[i] if i < len(self.ops) else FrameOp()
@@ -141,6 +158,10 @@ def stom_frame_ops(pred_tracks: np.ndarray, pred_visibility: np.ndarray, key_idx
             else:
                 rgba = [0, 0, 0, 0]
             rgba[3] = max(min(rgba[3], 148), 96)                           # :174
+            if not np.isfinite(trk[vis]).all():
+                # int(nan) / int(inf) raises in warp_point (:182-183); the caller's bare except keeps the frame (:93-100)
+                ops.append(FrameOp())
+                continue
             mask = np.zeros((h, w), dtype=np.uint8)
             for i, pt in enumerate(trk):                                   # :180-185
                 if vis[i]:
@@ -178,3 +199,47 @@ def stom_frame_ops(pred_tracks: np.ndarray, pred_visibility: np.ndarray, key_idx
         sy, zy = shift_from_flow(fy, h)
         ops.append(FrameOp(mode=_lib.FRAME_LAYER, sx=sx, sy=sy, zx=zx, zy=zy))
     return ops
+
+
+def stom_frame_ops_device(pred_tracks: torch.Tensor, pred_visibility: torch.Tensor, key_idx: int, shape: str, h: int, w: int,
+                          layer_rgba: Optional[torch.Tensor] = None, stream=None) -> Tuple[torch.Tensor, int]:
+    """``stom_frame_ops`` without the host: the same placement policy (STOM.py:72-141) computed by
+    csrc/stom_policy.cu from the tracker's CUDA outputs ``pred_tracks [T,N,2]`` fp32 (x, y) and
+    ``pred_visibility [T,N]`` (bool/uint8).  Returns ``(device_ops, circle_r)`` for
+    ``OverlaySpec(device_ops=..., device_ops_circle_r=...)``: a uint8 CUDA tensor [T, 36] of
+    b200vit_frame_op records, and the shared circle radius (-1 for non-mask shapes).  No device->host copy,
+    no synchronisation: the ops are consumed by the overlay kernel on the same stream."""
+    if not (pred_tracks.is_cuda and pred_visibility.is_cuda):
+        raise ValueError("stom_frame_ops_device takes CUDA tensors (use stom_frame_ops for host arrays)")
+    if pred_tracks.dim() != 3 or pred_tracks.shape[2] != 2 or tuple(pred_visibility.shape) != tuple(pred_tracks.shape[:2]):
+        raise ValueError("pred_tracks must be [T,N,2] and pred_visibility [T,N]")
+    trk = pred_tracks.to(torch.float32).contiguous()
+    vis = pred_visibility.to(torch.uint8).contiguous()
+    t, n = int(trk.shape[0]), int(trk.shape[1])
+    mask_shape = shape in ("mask", "mask contour")
+    lay_ptr = None
+    if mask_shape:
+        if layer_rgba is None or not layer_rgba.is_cuda or layer_rgba.dtype != torch.uint8 or tuple(layer_rgba.shape) != (h, w, 4):
+            raise ValueError("mask shapes need the CUDA uint8 RGBA layer [h,w,4]")
+        layer_rgba = layer_rgba.contiguous()
+        lay_ptr = layer_rgba.data_ptr()
+    l = _lib.lib()
+    ws_bytes = int(l.b200vit_stom_policy_workspace_bytes(t, n, h, w))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=trk.device)
+    ops = torch.empty((t, FRAME_OP_BYTES), dtype=torch.uint8, device=trk.device)
+    s = stream if stream is not None else torch.cuda.current_stream(trk.device).cuda_stream
+    _lib.check(l.b200vit_stom_policy(trk.data_ptr(), vis.data_ptr(), t, n, int(key_idx), int(mask_shape), int(h), int(w),
+                                     lay_ptr, ops.data_ptr(), ws.data_ptr(), ws_bytes, s), "stom_policy")
+    ops._keep = (trk, vis, ws, layer_rgba)  # inputs stay alive until the enqueued kernels have consumed them
+    return ops, (min(h, w) // 20 if mask_shape else -1)
+
+
+def frame_ops_from_bytes(raw: np.ndarray) -> List[FrameOp]:
+    """Decode a [T,36] uint8 array of b200vit_frame_op records (e.g. ``device_ops.cpu().numpy()``)."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8).reshape(-1, FRAME_OP_BYTES)
+    out = []
+    for rec in raw:
+        iv = rec[:32].view(np.int32)
+        out.append(FrameOp(mode=int(iv[0]), sx=int(iv[1]), sy=int(iv[2]), zx=int(iv[3]), zy=int(iv[4]), cx=int(iv[5]),
+                           cy=int(iv[6]), r=int(iv[7]), rgba=tuple(int(v) for v in rec[32:36])))
+    return out

@@ -78,6 +78,66 @@ def gen_overlay():
     np.savez_compressed(os.path.join(HERE, "overlay_boxes.npz"), boxes=boxes, layers=np.stack(outs))
 
 
+
+def policy_case(rng, h, w, t, n, key_idx, shape):
+    """Synthetic tracker output around a prompt: a common per-frame motion + jitter, outliers, frames with few
+    visible points, one frame with none, one with a non-finite visible coordinate."""
+    from PIL import Image, ImageDraw
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = np.stack([((xx * 3 + yy * 2 + 17 * i) % 256).astype(np.uint8)[..., None].repeat(3, 2) for i in range(t)])
+    frames[..., 1] = 255 - frames[..., 1]
+    vip = Image.new("RGBA", (w, h), (0, 0, 0, 0))
+    d = ImageDraw.Draw(vip)
+    if shape == "mask":
+        d.ellipse([(w // 3, h // 4), (w // 3 + w // 4, h // 4 + h // 3)], fill=(0, 255, 0, 160))
+    else:
+        d.rectangle([(w // 4, h // 5), (w // 4 + w // 3, h // 5 + h // 2)], outline=(255, 0, 0, 200), width=3)
+    layer = np.array(vip)
+    base = np.stack([rng.uniform(w * 0.3, w * 0.6, n), rng.uniform(h * 0.25, h * 0.6, n)], axis=1)
+    tracks = np.zeros((t, n, 2), dtype=np.float32)
+    vis = np.ones((t, n), dtype=bool)
+    for i in range(t):
+        motion = np.array([(i - key_idx) * 2.3 - 0.4 * (i % 3), (key_idx - i) * 1.7 + 0.3])
+        tracks[i] = (base + motion + rng.normal(0, 0.4, (n, 2))).astype(np.float32)
+        out = rng.random(n) < 0.1
+        tracks[i][out] += rng.normal(0, 25, (int(out.sum()), 2)).astype(np.float32)
+        vis[i] = rng.random(n) < 0.85
+    tracks[key_idx] = base.astype(np.float32)
+    if t > 3:
+        vis[(key_idx + 1) % t] = rng.random(n) < 0.3      # too few visible -> untouched
+        vis[(key_idx + 2) % t] = False                     # none visible
+    if t > 5:
+        j = (key_idx + 3) % t
+        k = int(np.nonzero(vis[j])[0][0])
+        tracks[j, k, 0] = np.nan                           # visible NaN: mask shapes raise -> untouched; others -> NaN mean
+    if t > 6:
+        tracks[(key_idx + 4) % t] += np.float32(-0.6)      # a flow that truncates toward zero at the border
+    return frames, layer, tracks, vis
+
+
+def gen_policy():
+    """STOM.propagate_in_video (the reference's own function, tracker stubbed) on synthetic tracks."""
+    from PIL import Image
+    STOM = import_reference_stom()
+    stom = STOM.__new__(STOM)
+    rng = np.random.default_rng(11)
+    out = {}
+    cases = [("rect_a", 75, 90, 8, 37, 2, "rectangle"), ("rect_b", 84, 56, 7, 200, 0, "scribble"),
+             ("mask_odd", 150, 135, 8, 60, 3, "mask"), ("mask_even", 150, 180, 7, 45, 6, "mask contour"),
+             ("mask_small", 60, 90, 5, 9, 1, "mask")]
+    for name, h, w, t, n, key_idx, shape in cases:
+        frames, layer, tracks, vis = policy_case(rng, h, w, t, n, key_idx, shape)
+        stom.track_in_video = lambda fr, vip, idx, save_path, tr=tracks, vi=vis: (tr[None].copy(), vi[None].copy())
+        pil_frames = [Image.fromarray(f, "RGB") for f in frames]
+        res = stom.propagate_in_video(pil_frames, Image.fromarray(layer, "RGBA"), key_idx, shape=shape)
+        out[name + "_frames"] = frames
+        out[name + "_layer"] = layer
+        out[name + "_tracks"] = tracks
+        out[name + "_vis"] = vis
+        out[name + "_meta"] = np.array([key_idx, 1 if shape in ("mask", "mask contour") else 0], dtype=np.int64)
+        out[name + "_out"] = np.stack([np.array(im.convert("RGB")) for im in res])
+    np.savez_compressed(os.path.join(HERE, "stom_policy.npz"), **out)
+
 def gen_patchify():
     from oracle import hf_ref
     fr = hf_ref.synthetic_frames(3, 56, 84, clip_id=3)   # odd T: exercises the pad-by-repeat
@@ -112,7 +172,12 @@ def gen_tower():
 
 
 if __name__ == "__main__":
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "policy":
+        gen_policy()
+        sys.exit(0)
     gen_overlay()
+    gen_policy()
     gen_patchify()
     gen_index()
     gen_tower()
