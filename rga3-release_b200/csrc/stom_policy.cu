@@ -232,13 +232,16 @@ stom_flow_kernel(const float* __restrict__ tracks, const uint8_t* __restrict__ v
 // ------------------------------------------------------------------ point policy (mask shapes)
 // frame_state[f]: 0 = proceed, 1 = leave the frame untouched (too few visible tracks :165-166, or a visible
 // non-finite coordinate, where the reference raises and its caller keeps the frame :93-100)
-__global__ void __launch_bounds__(POLICY_THREADS)
+constexpr int POINTS_PER_BLOCK = 32;
+
+__global__ void __launch_bounds__(256)
 stom_points_kernel(const float* __restrict__ tracks, const uint8_t* __restrict__ vis, int n, int key_idx, int h, int w,
                    SeRows se, uint8_t* __restrict__ dil, int32_t* __restrict__ frame_state) {
-  const int f = blockIdx.x;
+  const int f = blockIdx.y;
   if (f == key_idx) return;
   const float* trk = tracks + static_cast<size_t>(f) * n * 2;
   const uint8_t* v = vis + static_cast<size_t>(f) * n;
+  // every block of a frame re-derives the frame's verdict (n <= 16384 bytes to scan) instead of waiting for one
   int cnt = 0, bad = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     if (v[i]) {
@@ -250,17 +253,16 @@ stom_points_kernel(const float* __restrict__ tracks, const uint8_t* __restrict__
   __syncthreads();
   if (cnt) atomicAdd(&s_cnt, cnt);
   bad = __syncthreads_or(bad);  // also orders the atomics before the read below
-  if (s_cnt < n / 2 || bad) {
-    if (threadIdx.x == 0) frame_state[f] = 1;
-    return;
-  }
-  if (threadIdx.x == 0) frame_state[f] = 0;
+  const bool skip = s_cnt < n / 2 || bad;
+  if (blockIdx.x == 0 && threadIdx.x == 0) frame_state[f] = skip ? 1 : 0;
+  if (skip) return;
   // dilation of the point mask, stamped point by point: a point at (row, col) sets dst(row - (i - a), col - (j - a))
-  // for every element (i, j) of the structuring element
+  // for every element (i, j) of the structuring element.  All writers store 1, so overlaps need no ordering.
   uint8_t* d = dil + static_cast<size_t>(f) * h * w;
-  const int work = n * se.k;
+  const int p0 = blockIdx.x * POINTS_PER_BLOCK;
+  const int work = min(POINTS_PER_BLOCK, n - p0) * se.k;
   for (int idx = threadIdx.x; idx < work; idx += blockDim.x) {
-    const int i = idx / se.k, si = idx - i * se.k;
+    const int i = p0 + idx / se.k, si = idx % se.k;
     if (!v[i] || se.j1[si] >= se.j2[si]) continue;
     const float px = trk[2 * i + 1], py = trk[2 * i];  // the reference's x is the ROW (:181-185)
     if (fabsf(px) >= 1.0e9f || fabsf(py) >= 1.0e9f) continue;
@@ -474,7 +476,10 @@ extern "C" int b200vit_stom_policy(const float* d_tracks, const uint8_t* d_vis, 
   B200_CUDA_OK(cudaMemsetAsync(state, 0, static_cast<size_t>(t_frames) * sizeof(int32_t), stream));
   B200_CUDA_OK(cudaMemsetAsync(first, 0xff, sizeof(unsigned int), stream));
   stom_first_alpha_kernel<<<64, 256, 0, stream>>>(d_layer_rgba, h * w, first);
-  stom_points_kernel<<<t_frames, POLICY_THREADS, 0, stream>>>(d_tracks, d_vis, n_points, key_idx, h, w, se, dil, state);
+  if (n_points > 0) {
+    const dim3 pgrid((n_points + POINTS_PER_BLOCK - 1) / POINTS_PER_BLOCK, t_frames);
+    stom_points_kernel<<<pgrid, 256, 0, stream>>>(d_tracks, d_vis, n_points, key_idx, h, w, se, dil, state);
+  }
   stom_prefix_kernel<<<dim3(h, t_frames), 256, 0, stream>>>(dil, h, w, pre);
   stom_erode_moments_kernel<<<dim3(h, t_frames), 256, 0, stream>>>(pre, h, w, se, state, key_idx, moments);
   stom_points_finalize_kernel<<<(t_frames + 127) / 128, 128, 0, stream>>>(d_layer_rgba, first, moments, state, t_frames,
