@@ -184,7 +184,11 @@ overlay_patchify_kernel(const __grid_constant__ PatchParams p, const __grid_cons
 // into the patch layout in shared memory and leave as one contiguous, 16-byte-vectorised block.
 constexpr int SP = 14, STPS = 2, SMG = 2, SG = 2;           // geometry, groups per block
 constexpr int SCOLS = 3 * STPS * SP * SP;                   // 1176
-constexpr int STRIP_SMEM = SG * SMG * SMG * SCOLS * 2;      // 18,816 B
+constexpr int STRIP_OUT_BYTES = SG * SMG * SMG * SCOLS * 2; // 18,816 B  patch-layout bf16 block
+constexpr int STRIP_RH = SP * SMG;                          // 28 pixel rows per strip
+constexpr int STRIP_ROW_BYTES = SG * STRIP_RH * 3;          // 168 B of RGB per staged pixel row
+constexpr int STRIP_IN_BYTES = STPS * STRIP_RH * STRIP_ROW_BYTES;  // 9,408 B  staged uint8 pixels
+constexpr int STRIP_SMEM = STRIP_OUT_BYTES + STRIP_IN_BYTES;
 
 template <bool HAS_OVERLAY>
 __global__ void __launch_bounds__(256)
@@ -193,48 +197,66 @@ overlay_patchify_strip_kernel(const __grid_constant__ PatchParams p, const __gri
   griddep_launch_dependents();
   extern __shared__ __align__(16) uint8_t strip_raw[];
   uint16_t* out_s = reinterpret_cast<uint16_t*>(strip_raw);
+  uint8_t* in_s = strip_raw + STRIP_OUT_BYTES;
   __shared__ uint16_t lut[3 * 256];
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = c_norm_lut[i];
-  __syncthreads();
-  griddep_wait();  // the output buffer may still be read by the previous forward's patch-embed GEMM
+  constexpr int RH = STRIP_RH;
   const int gw2 = p.gw / SMG, gh2 = p.gh / SMG;
   const int bw0 = blockIdx.x * SG;
   const int groups = min(SG, gw2 - bw0);
   const int bh = blockIdx.y;
   const int tt = blockIdx.z + static_cast<int>(p.row_base / (static_cast<int64_t>(p.gh) * p.gw));  // absolute temporal index
-  constexpr int RH = SP * SMG;          // 28 pixel rows per strip
   const int rw = groups * RH;           // pixel columns of this block
-  const int npx = STPS * RH * rw;
+  // stage the block's pixels with 4-byte coalesced loads (rows of rw*3 contiguous bytes; every row start is 4-byte
+  // aligned because W and the block's first column are multiples of 28): all loads of a thread are independent
+  {
+    const int row_words = rw * 3 / 4;
+    const int y0 = bh * RH, x0 = bw0 * RH;
+    for (int r = threadIdx.x >> 6; r < STPS * RH; r += 4) {
+      const int tp = r / RH, yy = r - tp * RH;
+      const int f = min(tt * STPS + tp, p.t_total - 1);  // odd T: repeat the last frame (HF videoproc :245-249)
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(
+          p.frames + ((static_cast<size_t>(f - p.frame_base) * p.h + (y0 + yy)) * p.w + x0) * 3);
+      const int wi = threadIdx.x & 63;
+      if (wi < row_words) reinterpret_cast<uint32_t*>(in_s + r * STRIP_ROW_BYTES)[wi] = __ldg(src + wi);
+    }
+  }
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = c_norm_lut[i];
   FrameOpDev fop[STPS];  // the ops of this block's STPS frames
   if (HAS_OVERLAY) {
 #pragma unroll
     for (int tp = 0; tp < STPS; ++tp) fop[tp] = frame_op_at(ov, min(tt * STPS + tp, p.t_total - 1) - p.frame_base);
   }
-#pragma unroll 4
-  for (int idx = threadIdx.x; idx < npx; idx += blockDim.x) {
-    const int tp = idx / (RH * rw);
-    const int rem = idx - tp * (RH * rw);
-    const int yy = rem / rw, xx = rem - yy * rw;
-    const int f = min(tt * STPS + tp, p.t_total - 1);  // odd T: repeat the last frame (HF videoproc :245-249)
-    const int y = bh * RH + yy, x = bw0 * RH + xx;
-    const uint8_t* px = p.frames + ((static_cast<size_t>(f - p.frame_base) * p.h + y) * p.w + x) * 3;
-    uint32_t d0 = __ldg(px), d1 = __ldg(px + 1), d2 = __ldg(px + 2);
-    if (HAS_OVERLAY) {
-      const uint32_t sv = overlay_at(ov, fop[tp], p.h, p.w, y, x);
-      const uint32_t a = sv >> 24;
-      if (a) {
-        d0 = composite_ch(d0, sv & 0xffu, a);
-        d1 = composite_ch(d1, (sv >> 8) & 0xffu, a);
-        d2 = composite_ch(d2, (sv >> 16) & 0xffu, a);
+  __syncthreads();
+  griddep_wait();  // the output buffer may still be read by the previous forward's patch-embed GEMM
+  // one thread = one pixel column (64 lanes, rw <= 56 used) x every 4th pixel row: no index divisions in the loop
+  const int xx = threadIdx.x & 63;
+  if (xx < rw) {
+    const int x = bw0 * RH + xx;
+    const int g = xx / RH, xg = xx - g * RH;
+    const int col_part = (g * SMG * SMG + xg / SP) * SCOLS + (xg % SP);
+#pragma unroll
+    for (int tp = 0; tp < STPS; ++tp) {
+#pragma unroll 2
+      for (int yy = threadIdx.x >> 6; yy < RH; yy += 4) {
+        const uint8_t* px = in_s + (tp * RH + yy) * STRIP_ROW_BYTES + xx * 3;
+        uint32_t d0 = px[0], d1 = px[1], d2 = px[2];
+        if (HAS_OVERLAY) {
+          const uint32_t sv = overlay_at(ov, fop[tp], p.h, p.w, bh * RH + yy, x);
+          const uint32_t a = sv >> 24;
+          if (a) {
+            d0 = composite_ch(d0, sv & 0xffu, a);
+            d1 = composite_ch(d1, (sv >> 8) & 0xffu, a);
+            d2 = composite_ch(d2, (sv >> 16) & 0xffu, a);
+          }
+        }
+        const int half = yy >= SP ? 1 : 0;  // mi = (yy / SP) * SMG + xg / SP
+        const int ph = yy - half * SP;
+        uint16_t* dst = out_s + col_part + half * SMG * SCOLS + tp * SP * SP + ph * SP;
+        dst[0] = lut[d0];
+        dst[STPS * SP * SP] = lut[256 + d1];
+        dst[2 * STPS * SP * SP] = lut[512 + d2];
       }
     }
-    const int g = xx / RH, xg = xx - g * RH;
-    const int mi = (yy / SP) * SMG + xg / SP;
-    const int ph = yy % SP, pw = xg % SP;
-    uint16_t* dst = out_s + (g * SMG * SMG + mi) * SCOLS + tp * SP * SP + ph * SP + pw;
-    dst[0] = lut[d0];
-    dst[STPS * SP * SP] = lut[256 + d1];
-    dst[2 * STPS * SP * SP] = lut[512 + d2];
   }
   __syncthreads();
   const int64_t row0 = (static_cast<int64_t>(blockIdx.z) * gh2 + bh) * gw2 * SMG * SMG + static_cast<int64_t>(bw0) * SMG * SMG;
@@ -397,7 +419,7 @@ int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov,
       const int grid = static_cast<int>((threads + 255) / 256);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_bf16) + p.row_base * cols;
       const bool has_ov = ov != nullptr && (ov->h_ops != nullptr || ov->d_ops != nullptr);
-      if (patch == SP && tps == STPS && merge == SMG) {
+      if (patch == SP && tps == STPS && merge == SMG && (reinterpret_cast<uintptr_t>(p.frames) & 3) == 0) {
         static bool attr_set = false;
         if (!attr_set) {
           B200_CUDA_OK(cudaFuncSetAttribute(overlay_patchify_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
