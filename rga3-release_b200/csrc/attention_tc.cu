@@ -194,26 +194,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
           }
         }
       } else {
-        for (int hl = 0; hl < n_hl; ++hl)
-          for (int j = 0; j < nblk; ++j)
+        // Independent streams, single-buffered Q/K/V each: issue whichever buffer has been released instead of walking
+        // the streams in a fixed order (a stream waiting for its P.V to free V must not hold back the other stream's
+        // next Q/K, which were free since that stream's Q.K^T).  Per stream: it = hl * nblk + j.
+        const int n_it = n_hl * nblk;
+        int next_k[QTILES], next_v[QTILES];
 #pragma unroll
-            for (int t = 0; t < QTILES; ++t) {
+        for (int t = 0; t < QTILES; ++t) next_k[t] = next_v[t] = 0;
+        int remaining = 2 * QTILES * n_it;
+        const long long t0 = clock64();
+        while (remaining > 0) {
+          bool progressed = false;
+#pragma unroll
+          for (int t = 0; t < QTILES; ++t) {
+            int it = next_k[t];
+            if (it < n_it) {
+              const int hl = it / nblk, j = it - hl * nblk;
               const int head = head0 + hl * QTILES + t;
-              const int it = hl * nblk + j;
-              const uint32_t par = (it & 1) ^ 1;
-              const int row = tile.kv_row0 + j * KVB;
-              if (j == 0) {
-                mbar_wait(&q_empty[t], (hl & 1) ^ 1);
-                mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
-                load_tile(smem + L::OFF_Q + t * TILE_BYTES, &q_full[t], head * HD, tile.q_row0);
+              const bool need_q = j == 0;
+              if (mbar_test(&k_empty[t], (it & 1) ^ 1) && (!need_q || mbar_test(&q_empty[t], (hl & 1) ^ 1))) {
+                if (need_q) {
+                  mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+                  load_tile(smem + L::OFF_Q + t * TILE_BYTES, &q_full[t], head * HD, tile.q_row0);
+                }
+                mbar_arrive_expect_tx(&k_full[t], TILE_BYTES);
+                load_tile(smem + L::OFF_K + t * TILE_BYTES, &k_full[t], D + head * HD, tile.kv_row0 + j * KVB);
+                next_k[t] = it + 1;
+                --remaining;
+                progressed = true;
               }
-              mbar_wait(&k_empty[t], par);
-              mbar_arrive_expect_tx(&k_full[t], TILE_BYTES);
-              load_tile(smem + L::OFF_K + t * TILE_BYTES, &k_full[t], D + head * HD, row);
-              mbar_wait(&v_empty[t], par);
-              mbar_arrive_expect_tx(&v_full[t], V_TILE_BYTES);
-              load_v(smem + L::OFF_V + t * V_TILE_BYTES, &v_full[t], 2 * D + head * HD, row);
             }
+            it = next_v[t];
+            if (it < n_it && mbar_test(&v_empty[t], (it & 1) ^ 1)) {
+              const int hl = it / nblk, j = it - hl * nblk;
+              const int head = head0 + hl * QTILES + t;
+              mbar_arrive_expect_tx(&v_full[t], V_TILE_BYTES);
+              load_v(smem + L::OFF_V + t * V_TILE_BYTES, &v_full[t], 2 * D + head * HD, tile.kv_row0 + j * KVB);
+              next_v[t] = it + 1;
+              --remaining;
+              progressed = true;
+            }
+          }
+          if (!progressed) {
+            __nanosleep(40);
+            if (clock64() - t0 > 8000000000ll) {
+              printf("b200vit: attention loader timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
+              __trap();
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
