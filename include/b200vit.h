@@ -172,6 +172,13 @@ int b200vit_profile_read(b200vit_plan* plan, float* h_ms_by_kind, int32_t* h_cou
 /* Overlay only: composited uint8 frames [T,H,W,3] (bit-exact vs PIL).         */
 int b200vit_overlay_composite(const b200vit_frames* frames, const b200vit_overlay* overlay, uint8_t* d_out,
                               b200vit_stream stream);
+/* Frame resize ahead of the overlay: Pillow's bicubic Image.resize on uint8 RGB frames,
+ * bit for bit -- what qwen_vl_utils.fetch_image does to every frame after smart_resize (reference call sites
+ * app.py:296, :417, utils/dataset.py:76).  d_in [T,h_in,w_in,3] -> d_out [T,h_out,w_out,3]; w_out % 4 == 0.       */
+size_t b200vit_resize_workspace_bytes(int32_t t, int32_t h_in, int32_t w_in, int32_t h_out, int32_t w_out);
+int b200vit_resize_bicubic(const uint8_t* d_in, int32_t t, int32_t h_in, int32_t w_in, uint8_t* d_out, int32_t h_out,
+                           int32_t w_out, void* d_workspace, size_t workspace_bytes, b200vit_stream stream);
+
 /* STOM placement policy on the device (model/STOM.py:72-141 after the tracker): from tracker outputs
  * d_tracks fp32 [T,N,2] (x,y) and d_vis u8 [T,N] (non-zero = visible) to one frame op per frame in d_ops
  * (DEVICE array [T], the d_ops of b200vit_overlay), without a host round trip:

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200vit.so")
-SOURCES = ["common.cu", "gemm.cu", "attention_tc.cu", "elementwise.cu", "overlay.cu", "stom_policy.cu", "api.cu"]
+SOURCES = ["common.cu", "gemm.cu", "attention_tc.cu", "elementwise.cu", "overlay.cu", "stom_policy.cu", "resize.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"] + os.environ.get("B200VIT_NVCC_EXTRA", "").split()
 

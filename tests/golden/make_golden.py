@@ -138,6 +138,31 @@ def gen_policy():
         out[name + "_out"] = np.stack([np.array(im.convert("RGB")) for im in res])
     np.savez_compressed(os.path.join(HERE, "stom_policy.npz"), **out)
 
+
+def gen_resize():
+    """PIL.Image.resize (default BICUBIC) -- the call qwen_vl_utils.fetch_image makes per frame -- and HF smart_resize."""
+    from PIL import Image
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import smart_resize
+    rng = np.random.default_rng(21)
+    out = {}
+    cases = [(45, 80, 28, 56), (36, 64, 56, 84), (90, 60, 112, 84), (61, 47, 28, 28), (72, 128, 72, 84), (50, 100, 84, 100)]
+    for i, (h, w, oh, ow) in enumerate(cases):
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = np.stack([(xx * 5 + yy * 3) % 256, (xx * yy) % 256, rng.integers(0, 256, (h, w))], axis=2).astype(np.uint8)
+        out[f"in{i}"] = img
+        out[f"out{i}"] = np.array(Image.fromarray(img, "RGB").resize((ow, oh)))
+    sizes = []
+    for _ in range(400):
+        h, w = int(rng.integers(20, 2400)), int(rng.integers(20, 2400))
+        mp = int(rng.choice([384 * 28 * 28, 336 * 28 * 28, 1280 * 28 * 28, 16384 * 28 * 28]))
+        mn = int(rng.choice([4 * 28 * 28, 56 * 56, 256 * 28 * 28]))
+        if max(h, w) / min(h, w) > 200:
+            continue
+        oh, ow = smart_resize(h, w, factor=28, min_pixels=mn, max_pixels=mp)
+        sizes.append((h, w, mn, mp, oh, ow))
+    out["smart_resize"] = np.asarray(sizes, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "resize_pil.npz"), **out)
+
 def gen_patchify():
     from oracle import hf_ref
     fr = hf_ref.synthetic_frames(3, 56, 84, clip_id=3)   # odd T: exercises the pad-by-repeat
@@ -176,8 +201,12 @@ if __name__ == "__main__":
     if only == "policy":
         gen_policy()
         sys.exit(0)
+    if only == "resize":
+        gen_resize()
+        sys.exit(0)
     gen_overlay()
     gen_policy()
+    gen_resize()
     gen_patchify()
     gen_index()
     gen_tower()
