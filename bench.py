@@ -109,15 +109,19 @@ def random_state_dict_gpu(tower, seed=0):
 _SAMPLER_SRC = r"""
 import sys, time, pynvml as nv
 idx, interval = int(sys.argv[1]), float(sys.argv[2])
+calls = sys.argv[3] if len(sys.argv) > 3 else "cpr"
 nv.nvmlInit()
 h = nv.nvmlDeviceGetHandleByIndex(idx)
 print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)   # ~4 ms per call: once, up front
 while True:
-    try:
-        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-    except Exception:
-        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(r), flush=True)
+    r = 0
+    if "r" in calls:
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    p = nv.nvmlDeviceGetPowerUsage(h) / 1000.0 if "p" in calls else 0.0
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), p, int(r), flush=True)
     time.sleep(interval)
 """
 
@@ -136,7 +140,8 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.phys), str(self.interval)],
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.phys), str(self.interval),
+                                          os.environ.get("BENCH_SAMPLER_CALLS", "cpr")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             first = self.proc.stdout.readline().split()      # blocks until NVML is up in the child
             self.max_mhz = float(first[1]) if len(first) == 2 and first[0] == "max" else None
@@ -322,17 +327,35 @@ def main():
     torch.cuda.synchronize(dev)
     est_total = (time.perf_counter() - t_w) * args.steps
     barrier()
-    # NVML reads on a GPU that is inside an NCCL-coupled loop cost every rank a few ms each (measured at N = 2:
-    # 10.97 ms/step unsampled, 12.6 with 4 samples in 0.36 s): with N > 1 take two samples per region, not a stream
-    sampler = ClockSampler(local_rank, interval=min(max(est_total / (5.0 if world == 1 else 2.5), 0.1), 2.0))
-    if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):
+    # Clocks.  N = 1: NVML (the recipe's nvidia-smi line) sampled in a separate process during the timed region.
+    # N > 1: NVML reads while the ranks are coupled through NCCL inflate the step by 15-90 % (measured at N = 2, 30 steps:
+    # 10.70 ms/step unsampled, 12.2-20.1 ms with 2-3 samples, whichever NVML call is made and whichever GPU is read), so
+    # the SM clock of the timed region comes from an in-kernel probe instead (b200vit_clock_probe: SM cycles per
+    # globaltimer nanosecond over 50 us, launched on a side stream every few steps), and throttle reasons / power are
+    # read through NVML during an immediate untimed repeat of the same loop.
+    use_probe = world > 1 and not os.environ.get("BENCH_NVML_IN_REGION")
+    sampler = ClockSampler(int(os.environ.get("BENCH_SAMPLER_GPU", local_rank)),
+                           interval=min(max(est_total / 5.0, 0.1), 2.0) if not use_probe else 0.1)
+    n_probe = 6
+    probe_every = max(args.steps // n_probe, 1)
+    probe_buf = torch.zeros((args.steps // probe_every + 1, 2), dtype=torch.int64, device=dev)
+    probe_stream = torch.cuda.Stream(dev, priority=-1)
+    probes = [0]
+
+    def maybe_probe(i):
+        if use_probe and rank == 0 and i % probe_every == probe_every // 2:
+            _lib.check(_lib.lib().b200vit_clock_probe(probe_buf[probes[0]].data_ptr(), 50000, probe_stream.cuda_stream), "probe")
+            probes[0] += 1
+
+    if rank == 0 and not use_probe and not os.environ.get("BENCH_NO_CLOCKS"):
         sampler.start()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     fork()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step_resident()
+        maybe_probe(i)
     drain()
     e1.record()
     barrier()
@@ -341,7 +364,31 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = None
+    if not use_probe:
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    else:
+        # untimed repeat of the same loop with the NVML sampler running: throttle reasons, power, NVML's own clock
+        if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):
+            sampler.start()
+        barrier()
+        r_wall0 = time.time()
+        fork()
+        for _ in range(min(args.steps, 30)):
+            step_resident()
+        drain()
+        barrier()
+        r_wall1 = time.time()
+        if rank == 0:
+            nv = sampler.stop(r_wall0, r_wall1)
+            pb = probe_buf[:probes[0]].cpu().numpy().astype(np.float64)
+            mhz = [c / ns * 1e3 for c, ns in pb if ns > 0]
+            clocks = {"sm_mhz": float(np.median(mhz)) if mhz else nv.get("sm_mhz"), "sm_max_mhz": nv.get("sm_max_mhz"),
+                      "reasons": nv.get("reasons", []), "samples": len(mhz),
+                      "source": "timed region: in-kernel probe (SM cycles / globaltimer ns over 50 us, every "
+                                f"{probe_every} steps); reasons/power: NVML during an untimed repeat of the loop "
+                                "(NVML reads inside the NCCL-coupled timed loop inflate the step time, see bench.py)",
+                      "nvml_repeat": {k: nv.get(k) for k in ("sm_mhz", "power_w_max", "samples")}}
 
     # ---- host cost of enqueueing one step: two steps into an empty queue (no back-pressure from the GPU)
     t_h = time.perf_counter()

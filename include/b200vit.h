@@ -172,6 +172,10 @@ int b200vit_profile_read(b200vit_plan* plan, float* h_ms_by_kind, int32_t* h_cou
 /* Overlay only: composited uint8 frames [T,H,W,3] (bit-exact vs PIL).         */
 int b200vit_overlay_composite(const b200vit_frames* frames, const b200vit_overlay* overlay, uint8_t* d_out,
                               b200vit_stream stream);
+/* Measurement aid: one thread spins for spin_ns (<= 1 ms) and writes {SM cycles, nanoseconds} of that interval to
+ * d_out2[2] -- the SM clock under load without an NVML read (bench.py, N > 1).                                     */
+int b200vit_clock_probe(uint64_t* d_out2, uint32_t spin_ns, b200vit_stream stream);
+
 /* Frame resize ahead of the overlay: Pillow's bicubic Image.resize on uint8 RGB frames,
  * bit for bit -- what qwen_vl_utils.fetch_image does to every frame after smart_resize (reference call sites
  * app.py:296, :417, utils/dataset.py:76).  d_in [T,h_in,w_in,3] -> d_out [T,h_out,w_out,3]; w_out % 4 == 0.       */

@@ -74,6 +74,7 @@ EXPORTS = {
     "b200vit_overlay_composite": (C.c_int, [C.POINTER(Frames), C.POINTER(Overlay), C.c_void_p, C.c_void_p]),
     "b200vit_overlay_patchify": (C.c_int, [C.POINTER(Frames), C.POINTER(Overlay), C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p]),
+    "b200vit_clock_probe": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200vit_resize_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "b200vit_resize_bicubic": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -142,3 +142,33 @@ int launch_cast_bf16(const void* in, int in_dtype, void* out, int64_t n, cudaStr
 }
 
 }  // namespace b200
+
+// ------------------------------------------------------------------ SM clock probe (measurement aid)
+// One thread spins for `spin_ns` of wall time and reports (SM cycles, nanoseconds) over that interval: the SM clock
+// the GPU actually runs at while other kernels execute, read without NVML (bench.py uses it for N > 1, where NVML
+// reads inside an NCCL-coupled loop perturb the measurement).
+namespace b200 {
+namespace {
+__global__ void clock_probe_kernel(unsigned long long* __restrict__ out, unsigned int spin_ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < spin_ns);
+  const long long c1 = clock64();
+  out[0] = static_cast<unsigned long long>(c1 - c0);
+  out[1] = t1 - t0;
+}
+}  // namespace
+}  // namespace b200
+
+extern "C" int b200vit_clock_probe(uint64_t* d_out2, uint32_t spin_ns, b200vit_stream stream) {
+  if (d_out2 == nullptr || (reinterpret_cast<uintptr_t>(d_out2) & 7)) return b200::fail(B200VIT_EINVAL, "clock_probe: bad output pointer");
+  if (spin_ns > 1000000u) spin_ns = 1000000u;
+  b200::clock_probe_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(d_out2), spin_ns);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+

@@ -338,3 +338,13 @@ def test_cast_fp16_and_tail():
     _lib.check(_lib.lib().b200vit_cast_to_bf16(x.data_ptr(), 1, out.data_ptr(), x.numel(), _stream()), "cast")
     torch.cuda.synchronize()
     assert torch.equal(out, x.to(torch.bfloat16))
+
+
+def test_clock_probe_reports_a_plausible_sm_clock():
+    buf = torch.zeros(2, dtype=torch.int64, device=DEV)
+    _lib.check(_lib.lib().b200vit_clock_probe(buf.data_ptr(), 50000, _stream()), "probe")
+    torch.cuda.synchronize()
+    cycles, ns = [int(v) for v in buf.cpu()]
+    assert 50000 <= ns < 5_000_000
+    assert 500.0 < cycles / ns * 1e3 < 2500.0          # MHz
+    assert _lib.lib().b200vit_clock_probe(None, 1000, _stream()) == -1
