@@ -401,6 +401,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer (every CTA) =====================
+#ifdef B200_GEMM_DBG_NOTMA
+      if (true) { griddep_wait(); } else  // measurement only: no loads at all, the MMAs run on whatever is in shared memory
+#endif
+      {
       // phase 1 (before the dependency wait): arm the first stages and start their B (weight) loads
       int pre = 0;
       {
@@ -450,6 +454,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
       }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
@@ -480,8 +485,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const uint32_t tacc = tmem_base + as * C::ACC_STRIDE;
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           GSTAMP(t_issue);
+#ifndef B200_GEMM_DBG_NOTMA
           mbar_wait(&full[s], ph);
           tc_fence_after();
+#endif
           GSTAMP(t_full);
           const uint32_t a_addr = smem_u32(sA + s * C::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
@@ -608,7 +615,11 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     if (rc) return rc;
     const int num_tiles = ((a.m + MT - 1) / MT) * ((a.n + BN - 1) / BN);
     const int sms = device_sm_count();
-    const int max_units = PAIR ? sms / 2 : sms;
+    int max_units = PAIR ? sms / 2 : sms;
+    if (const char* e = getenv("B200VIT_GEMM_MAX_UNITS")) {  // experiment: run on fewer SMs
+      const int lim = atoi(e);
+      if (lim > 0 && lim < max_units) max_units = lim;
+    }
     int units = num_tiles < max_units ? num_tiles : max_units;
     g.stream_k = 0;
     if (EPI == B200VIT_EPI_BIAS_RESIDUAL && stream_k_enabled()) {
