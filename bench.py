@@ -408,40 +408,15 @@ def main():
             a[1] += n
     tower.profile(grid, False)
 
-    # ---- end-to-end: pinned host frames in, host embeddings out, double-buffered on copy streams
-    out_host = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(2)]
-    fr_dev = [torch.empty_like(frames_dev) for _ in range(2)]
-    out_dev = [torch.empty_like(out) for _ in range(2)]
-    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    cur = torch.cuda.current_stream(dev)
+    # ---- end-to-end through the public feed API (rga3_release_b200.ClipPipeline): pinned host uint8 frames in, host
+    # embeddings out, H2D / D2H on their own streams, two clips in flight
+    pipe = vit.ClipPipeline(tower, tuple(frames_host.shape), depth=2, to_host=True,
+                            after_forward=(gather_out if do_gather else None))
 
     def e2e_loop(n):
-        ev_c = [None, None]
-        ev_d = [None, None]
-        for i in range(n):
-            b = i & 1
-            with torch.cuda.stream(s_h2d):
-                if ev_c[b] is not None:
-                    s_h2d.wait_event(ev_c[b])          # compute of step i-2 has consumed this input buffer
-                fr_dev[b].copy_(frames_host, non_blocking=True)
-                ev_h = torch.cuda.Event()
-                ev_h.record(s_h2d)
-            cur.wait_event(ev_h)
-            if ev_d[b] is not None:
-                cur.wait_event(ev_d[b])                # D2H of step i-2 has drained this output buffer
-            tower.forward_frames(fr_dev[b], overlay, out=out_dev[b])
-            if do_gather:
-                gather_out(out_dev[b])
-            ev_c[b] = torch.cuda.Event()
-            ev_c[b].record(cur)
-            with torch.cuda.stream(s_d2h):
-                s_d2h.wait_event(ev_c[b])
-                out_host[b].copy_(out_dev[b], non_blocking=True)
-                ev_d[b] = torch.cuda.Event()
-                ev_d[b].record(s_d2h)
-        for e in ev_d:
-            if e is not None:
-                cur.wait_event(e)
+        for _ in range(n):
+            pipe.submit(frames_host, overlay)
+        pipe.drain()                                   # the last results are in host memory
 
     e2e_loop(args.warmup)
     barrier()
@@ -482,7 +457,7 @@ def main():
             "pct_bf16_peak_sustained": total_flops / (step_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms_total * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": int(out.numel() * out.element_size()),
+                    "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
                     "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": launches * args.steps, "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -7,8 +7,9 @@ from ._lib import B200VitError, lib
 from .module import B200VisionTower, install, splice_span
 from .dist import gather_tokens, shard_clips, shard_slices
 from .preprocess import fit_frames, resize_frames, smart_resize
+from .pipeline import ClipPipeline
 from .overlay import (FrameOp, OverlaySpec, frame_ops_from_bytes, shift_from_flow, stom_frame_ops,
                       stom_frame_ops_device)
 
-__all__ = ["B200VisionTower", "install", "splice_span", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "stom_frame_ops_device", "frame_ops_from_bytes", "lib", "shard_clips", "shard_slices", "gather_tokens", "smart_resize", "resize_frames", "fit_frames",
+__all__ = ["B200VisionTower", "install", "splice_span", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "stom_frame_ops_device", "frame_ops_from_bytes", "lib", "shard_clips", "shard_slices", "gather_tokens", "smart_resize", "resize_frames", "fit_frames", "ClipPipeline",
            "B200VitError"]

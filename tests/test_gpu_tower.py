@@ -255,3 +255,28 @@ def test_forward_frames_odd_frame_count_and_fp32_pixels():
         o2 = t(torch.from_numpy(pv).to(DEV).to(dt), torch.from_numpy(grid))
         cos, rel = parity(o2, ref)
         assert cos >= COS_MIN and rel <= REL_MAX, (dt, cos, rel)
+
+
+def test_clip_pipeline_matches_direct_calls():
+    """ClipPipeline (overlapped H2D / compute / D2H, two clips in flight) returns, in order, exactly what
+    forward_frames returns for each clip."""
+    t, cfg, sd = make_tower(hf_ref.CFG_TINY)
+    T, H, W = 4, 56, 84
+    clips = [hf_ref.synthetic_frames(T, H, W, clip_id=i).pin_memory() for i in range(5)]
+    layer = overlay_ref.box_layer_ref(H, W, (10, 8, 70, 48), 3, (255, 0, 0, 200))
+    ops = [vit.FrameOp(mode=_lib.FRAME_LAYER, sx=i, sy=-i) for i in range(T)]
+    spec = vit.OverlaySpec.from_rgba(layer, ops)
+    direct = [t.forward_frames(c.to(DEV), spec if i % 2 else None).clone() for i, c in enumerate(clips)]
+    pipe = vit.ClipPipeline(t, (T, H, W, 3), depth=2)
+    got = []
+    for i, c in enumerate(clips):
+        r = pipe.submit(c, spec if i % 2 else None)
+        if r is not None:
+            got.append(r.clone())
+    got += [r.clone() for r in pipe.drain()]
+    assert len(got) == len(clips)
+    for a, b in zip(got, direct):
+        assert torch.equal(a, b.cpu())
+    assert pipe.h2d_bytes == T * H * W * 3 and pipe.d2h_bytes == direct[0].numel() * direct[0].element_size()
+    with pytest.raises(ValueError):
+        vit.ClipPipeline(t, (T, H, W, 3), depth=1)
