@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200VIT_VERSION 1
+#define B200VIT_VERSION 2
 
 enum {
   B200VIT_OK = 0,

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in b200vit.h but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.b200vit_version() == 1
+    assert lib.b200vit_version() == 2
 
 
 @pytest.mark.parametrize("grid", [[[2, 8, 12]], [[8, 32, 32]], [[1, 6, 10], [2, 18, 14]], [[1, 2, 2]], [[3, 48, 48]]])
