@@ -150,3 +150,21 @@ def test_gather_tokens_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/b200vit.h compiles as C99 (-pedantic: no C++ types cross the ABI) and a plain-C host program links
+    against libb200vit.so and builds a plan on the host (examples/c_abi_demo.c)."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    vit.lib()  # make sure the library exists (raises with the build hint otherwise)
+    libdir = os.path.join(ROOT, "rga3-release_b200")
+    exe = str(tmp_path / "c_abi_demo")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lb200vit", f"-Wl,-rpath,{libdir}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "b200vit version 2" in r.stdout and "workspace bytes: 222691328" in r.stdout
