@@ -54,7 +54,9 @@ struct PatchParams {
   int64_t rows;           // rows produced by this launch
 };
 
-__constant__ uint16_t c_norm_lut[3 * 256];  // bf16 bits of (v - 255*mean_c) / (255*std_c)
+// bf16 bits of (v - 255*mean_c) / (255*std_c).  Plain global memory, not __constant__: every thread reads a different entry when the
+// table is copied to shared memory, and the constant cache serialises divergent addresses (16 % of the kernel in ncu).
+__device__ uint16_t g_norm_lut[3 * 256];
 
 __device__ __forceinline__ uint32_t layer_at(const OverlayParams& ov, int h, int w, int y, int x) {
   if (y < 0 || y >= h || x < 0 || x >= w) return 0u;
@@ -129,7 +131,7 @@ overlay_patchify_kernel(const __grid_constant__ PatchParams p, const __grid_cons
                         __nv_bfloat16* __restrict__ out) {
   griddep_launch_dependents();
   __shared__ uint16_t lut[3 * 256];
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = c_norm_lut[i];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = g_norm_lut[i];
   __syncthreads();
   griddep_wait();  // the output buffer may still be read by the previous forward's patch-embed GEMM
   const int chunks = p.cols >> 3;
@@ -209,18 +211,29 @@ overlay_patchify_strip_kernel(const __grid_constant__ PatchParams p, const __gri
   // stage the block's pixels with 4-byte coalesced loads (rows of rw*3 contiguous bytes; every row start is 4-byte
   // aligned because W and the block's first column are multiples of 28): all loads of a thread are independent
   {
+    // every thread owns one word column of 14 staged rows: issue all 14 loads, then store (the kernel is latency-bound:
+    // 10 MB in, the 19 MB result stays in L2; a load->store loop left one request in flight per warp)
     const int row_words = rw * 3 / 4;
     const int y0 = bh * RH, x0 = bw0 * RH;
-    for (int r = threadIdx.x >> 6; r < STPS * RH; r += 4) {
+    const int wi = threadIdx.x & 63;
+    constexpr int NR = STPS * RH / 4;  // 14 rows per thread
+    uint32_t tmp[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int r = (threadIdx.x >> 6) + 4 * k;
       const int tp = r / RH, yy = r - tp * RH;
       const int f = min(tt * STPS + tp, p.t_total - 1);  // odd T: repeat the last frame (HF videoproc :245-249)
       const uint32_t* src = reinterpret_cast<const uint32_t*>(
           p.frames + ((static_cast<size_t>(f - p.frame_base) * p.h + (y0 + yy)) * p.w + x0) * 3);
-      const int wi = threadIdx.x & 63;
-      if (wi < row_words) reinterpret_cast<uint32_t*>(in_s + r * STRIP_ROW_BYTES)[wi] = __ldg(src + wi);
+      tmp[k] = wi < row_words ? __ldg(src + wi) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int r = (threadIdx.x >> 6) + 4 * k;
+      if (wi < row_words) reinterpret_cast<uint32_t*>(in_s + r * STRIP_ROW_BYTES)[wi] = tmp[k];
     }
   }
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = c_norm_lut[i];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = g_norm_lut[i];
   FrameOpDev fop[STPS];  // the ops of this block's STPS frames
   if (HAS_OVERLAY) {
 #pragma unroll
@@ -234,19 +247,28 @@ overlay_patchify_strip_kernel(const __grid_constant__ PatchParams p, const __gri
     const int x = bw0 * RH + xx;
     const int g = xx / RH, xg = xx - g * RH;
     const int col_part = (g * SMG * SMG + xg / SP) * SCOLS + (xg % SP);
+    constexpr int NP = RH / 4;  // 7 pixel rows per thread and frame
+    uint32_t sv[STPS][NP];
+    if (HAS_OVERLAY) {  // all layer look-ups of this thread first: independent loads in flight together
+#pragma unroll
+      for (int tp = 0; tp < STPS; ++tp)
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+          sv[tp][k] = overlay_at(ov, fop[tp], p.h, p.w, bh * RH + (threadIdx.x >> 6) + 4 * k, x);
+    }
 #pragma unroll
     for (int tp = 0; tp < STPS; ++tp) {
-#pragma unroll 2
-      for (int yy = threadIdx.x >> 6; yy < RH; yy += 4) {
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        const int yy = (threadIdx.x >> 6) + 4 * k;
         const uint8_t* px = in_s + (tp * RH + yy) * STRIP_ROW_BYTES + xx * 3;
         uint32_t d0 = px[0], d1 = px[1], d2 = px[2];
         if (HAS_OVERLAY) {
-          const uint32_t sv = overlay_at(ov, fop[tp], p.h, p.w, bh * RH + yy, x);
-          const uint32_t a = sv >> 24;
+          const uint32_t a = sv[tp][k] >> 24;
           if (a) {
-            d0 = composite_ch(d0, sv & 0xffu, a);
-            d1 = composite_ch(d1, (sv >> 8) & 0xffu, a);
-            d2 = composite_ch(d2, (sv >> 16) & 0xffu, a);
+            d0 = composite_ch(d0, sv[tp][k] & 0xffu, a);
+            d1 = composite_ch(d1, (sv[tp][k] >> 8) & 0xffu, a);
+            d2 = composite_ch(d2, (sv[tp][k] >> 16) & 0xffu, a);
           }
         }
         const int half = yy >= SP ? 1 : 0;  // mi = (yy / SP) * SMG + xg / SP
@@ -309,7 +331,7 @@ int upload_lut() {
       lut[c * 256 + v] = f32_to_bf16_rne(q);
     }
   }
-  B200_CUDA_OK(cudaMemcpyToSymbol(c_norm_lut, lut, sizeof(lut)));
+  B200_CUDA_OK(cudaMemcpyToSymbol(g_norm_lut, lut, sizeof(lut)));
   done = true;
   return 0;
 }
