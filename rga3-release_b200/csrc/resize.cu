@@ -107,14 +107,19 @@ resize_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int r
   const int nbytes = static_cast<int>(static_cast<int64_t>(last) * 3 - b0);
   const bool staged = span_bytes > 0 && nbytes <= span_bytes && aligned;
   if (staged) {
+    // all rows' loads of one word column are issued before any store: the pass is latency-bound otherwise (ncu: a
+    // load->store loop keeps one request in flight per warp)
     const int full = nbytes >> 2;
-    for (int r = 0; r < nrows; ++r) {
-      const uint8_t* src_row = src0 + r * row_bytes + b0;
-      uint8_t* dst_row = span + r * span_bytes;
-      for (int i = threadIdx.x; i < full; i += 256)
-        reinterpret_cast<uint32_t*>(dst_row)[i] = __ldg(reinterpret_cast<const uint32_t*>(src_row) + i);
-      for (int i = (full << 2) + threadIdx.x; i < nbytes; i += 256) dst_row[i] = __ldg(src_row + i);
+    for (int i = threadIdx.x; i < full; i += 256) {
+      uint32_t tmp[RESIZE_H_ROWS];
+#pragma unroll
+      for (int r = 0; r < RESIZE_H_ROWS; ++r)
+        tmp[r] = r < nrows ? __ldg(reinterpret_cast<const uint32_t*>(src0 + r * row_bytes + b0) + i) : 0u;
+#pragma unroll
+      for (int r = 0; r < RESIZE_H_ROWS; ++r) reinterpret_cast<uint32_t*>(span + r * span_bytes)[i] = tmp[r];
     }
+    for (int i = (full << 2) + threadIdx.x; i < nbytes; i += 256)
+      for (int r = 0; r < nrows; ++r) span[r * span_bytes + i] = __ldg(src0 + r * row_bytes + b0 + i);
     __syncthreads();
   }
   const int xo = xo0 + threadIdx.x;
@@ -169,13 +174,22 @@ resize_v_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int f
   const int32_t* k = kk + static_cast<size_t>(yo) * ksize;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (static_cast<size_t>(f) * h_in + ymin) * row_bytes) + wi;
   int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0, s3 = s0;
-  for (int y = 0; y < cnt; ++y) {
-    const int c = __ldg(k + y);
-    const uint32_t v = __ldg(src + static_cast<size_t>(y) * words);
-    s0 += static_cast<int>(v & 0xffu) * c;
-    s1 += static_cast<int>((v >> 8) & 0xffu) * c;
-    s2 += static_cast<int>((v >> 16) & 0xffu) * c;
-    s3 += static_cast<int>(v >> 24) * c;
+  for (int y0 = 0; y0 < cnt; y0 += 4) {  // four taps' loads in flight together (a zero coefficient pads the tail)
+    int c[4];
+    uint32_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool on = y0 + u < cnt;
+      c[u] = on ? __ldg(k + y0 + u) : 0;
+      v[u] = on ? __ldg(src + static_cast<size_t>(y0 + u) * words) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s0 += static_cast<int>(v[u] & 0xffu) * c[u];
+      s1 += static_cast<int>((v[u] >> 8) & 0xffu) * c[u];
+      s2 += static_cast<int>((v[u] >> 16) & 0xffu) * c[u];
+      s3 += static_cast<int>(v[u] >> 24) * c[u];
+    }
   }
   reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(f) * h_out + yo) * row_bytes)[wi] =
       clip8(s0) | (clip8(s1) << 8) | (clip8(s2) << 16) | (static_cast<uint32_t>(clip8(s3)) << 24);
