@@ -13,6 +13,7 @@ all arithmetic runs in the hand-written sm_100a kernels.  There is no fallback.
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -35,26 +36,21 @@ class _Holder(nn.Module):
 
 
 class _Plan:
-    """Owns one b200vit_plan plus its workspace / static buffers."""
+    """Owns one b200vit_plan (host + device index tables, launch memos).  The activation workspace is NOT per plan:
+    the tower keeps one per slot, sized for the largest grid seen, so a service that sees many resolutions does not
+    accumulate gigabytes of idle workspaces."""
 
-    def __init__(self, grid: Tuple[Tuple[int, int, int], ...], cfg_c, device):
+    def __init__(self, grid: Tuple[Tuple[int, int, int], ...], cfg_c, device, slot: int = 0):
         self.grid = grid
+        self.slot = slot
         arr = (C.c_int64 * (3 * len(grid)))(*[v for g in grid for v in g])
         handle = C.c_void_p()
         _lib.check(_lib.lib().b200vit_plan_create(arr, len(grid), C.byref(cfg_c), C.byref(handle)), "plan_create")
         self.handle = handle
         self.m = int(sum(t * h * w for t, h, w in grid))
         self.ws_bytes = int(_lib.lib().b200vit_workspace_bytes(handle))
-        self.workspace = None
         self.device = device
         self.graphs: Dict[str, tuple] = {}
-
-    def ensure_workspace(self):
-        if self.workspace is None:
-            self.workspace = torch.empty(self.ws_bytes + 1024, dtype=torch.uint8, device=self.device)
-            off = (-self.workspace.data_ptr()) % 1024
-            self.ws_ptr = self.workspace.data_ptr() + off
-        return self.ws_ptr
 
     def get(self, which: int, dtype) -> np.ndarray:
         n = int(_lib.lib().b200vit_plan_get(self.handle, which, None, 0))
@@ -84,8 +80,9 @@ class _Output:
 
 class B200VisionTower(nn.Module):
     def __init__(self, config, device="cuda", dtype=torch.bfloat16, return_dict: Optional[bool] = None,
-                 use_cuda_graph: bool = False, output_fp32: bool = False):
+                 use_cuda_graph: bool = False, output_fp32: bool = False, max_plans: int = 32):
         super().__init__()
+        self.max_plans = max(int(max_plans), 1)
         g = (lambda k, d=None: getattr(config, k, d)) if not isinstance(config, dict) else (lambda k, d=None: config.get(k, d))
         self.config = config
         self.depth = g("depth", 32)
@@ -140,7 +137,8 @@ class B200VisionTower(nn.Module):
         for j, v in enumerate(self.fullatt_block_indexes):
             self._cfg_c.fullatt[j] = int(v)
         self._packed = None
-        self._plans: Dict[tuple, _Plan] = {}
+        self._plans: "OrderedDict[tuple, _Plan]" = OrderedDict()   # LRU, at most max_plans entries
+        self._workspaces: Dict[int, tuple] = {}                     # slot -> (tensor, aligned pointer, usable bytes)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # ---- HF-style attributes
@@ -224,9 +222,25 @@ class B200VisionTower(nn.Module):
         key = (grid, int(slot))
         p = self._plans.get(key)
         if p is None:
-            p = _Plan(grid, self._cfg_c, self._device)
+            p = _Plan(grid, self._cfg_c, self._device, int(slot))
             self._plans[key] = p
+            while len(self._plans) > self.max_plans:       # least recently used first; never the one just made
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
         return p
+
+    def _workspace(self, plan: _Plan) -> int:
+        """1024-byte aligned workspace pointer for this plan's slot, grown (never shrunk) to the largest request."""
+        ws = self._workspaces.get(plan.slot)
+        if ws is None or ws[2] < plan.ws_bytes:
+            t = torch.empty(plan.ws_bytes + 1024, dtype=torch.uint8, device=self._device)
+            ptr = t.data_ptr() + ((-t.data_ptr()) % 1024)
+            self._workspaces[plan.slot] = ws = (t, ptr, plan.ws_bytes)
+            for (_, s), q in self._plans.items():           # captured graphs point into the old buffer
+                if s == plan.slot:
+                    q.graphs.clear()
+        return ws[1]
 
     # ---- the hot path
     def _run(self, plan: _Plan, pixel_values, frames_c, overlay_c, out, last_hidden):
@@ -238,7 +252,7 @@ class B200VisionTower(nn.Module):
             C.byref(overlay_c) if overlay_c is not None else None,
             out.data_ptr(), 1 if out.dtype == torch.float32 else 0,
             last_hidden.data_ptr() if last_hidden is not None else None,
-            plan.ensure_workspace(), plan.ws_bytes, stream)
+            self._workspace(plan), plan.ws_bytes, stream)
         _lib.check(rc, "b200vit_forward")
 
     def _wrap(self, out, last_hidden):

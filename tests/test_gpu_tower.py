@@ -280,3 +280,21 @@ def test_clip_pipeline_matches_direct_calls():
     assert pipe.h2d_bytes == T * H * W * 3 and pipe.d2h_bytes == direct[0].numel() * direct[0].element_size()
     with pytest.raises(ValueError):
         vit.ClipPipeline(t, (T, H, W, 3), depth=1)
+
+
+def test_shared_workspace_and_plan_lru_across_many_grids():
+    """One workspace per slot (grown to the largest grid) and a bounded plan cache: alternating resolutions gives the
+    same embeddings as a fresh tower per grid, and memory does not pile up per grid."""
+    t, cfg, sd = make_tower(hf_ref.CFG_TINY, max_plans=3)
+    grids = [[[1, 4, 6]], [[2, 8, 12]], [[1, 2, 2]], [[3, 6, 10]], [[1, 4, 6]], [[2, 8, 12]], [[1, 10, 8]], [[1, 2, 2]]]
+    outs = []
+    for i, g in enumerate(grids):
+        m = sum(a * b * c for a, b, c in g)
+        x = torch.randn(m, 1176, generator=torch.Generator().manual_seed(100 + i)).to(DEV)
+        outs.append((g, x, t(x, g).clone()))
+        assert len(t._plans) <= 3 and len(t._workspaces) == 1
+    ws_bytes = t._workspaces[0][2]
+    assert ws_bytes == max(vit.B200VisionTower(dict(hf_ref.CFG_TINY), device="cpu").plan_for(g).ws_bytes for g in grids)
+    for g, x, out in outs:
+        fresh, _, _ = make_tower(hf_ref.CFG_TINY)
+        assert torch.equal(fresh(x, g), out), g
