@@ -153,6 +153,18 @@ class B200VisionTower(nn.Module):
     def _invalidate(self):
         self._packed = None
 
+    def _apply(self, fn, *args, **kwargs):
+        """`.to()`, `.cuda()`, `.half()` ...: the HF-named parameters move or change dtype, so the packed copies (and,
+        on a device change, every plan and workspace) are rebuilt lazily by the next forward."""
+        out = super()._apply(fn, *args, **kwargs)
+        p = next(self.parameters(), None)
+        if p is not None and p.device != self._device:
+            self._device = p.device
+            self._plans.clear()
+            self._workspaces.clear()
+        self._invalidate()
+        return out
+
     @classmethod
     def from_hf(cls, hf_tower, **kw):
         """Build from an instantiated HF tower (copies its weights)."""

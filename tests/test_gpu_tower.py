@@ -298,3 +298,18 @@ def test_shared_workspace_and_plan_lru_across_many_grids():
     for g, x, out in outs:
         fresh, _, _ = make_tower(hf_ref.CFG_TINY)
         assert torch.equal(fresh(x, g), out), g
+
+
+def test_module_apply_keeps_the_tower_consistent():
+    """`.to(dtype)` / `.to(device)` on the nn.Module re-packs the weights instead of running on stale copies."""
+    t, cfg, sd = make_tower(hf_ref.CFG_TINY)
+    g = [[2, 4, 6]]
+    x = torch.randn(48, 1176, generator=torch.Generator().manual_seed(3)).to(DEV)
+    ref = t(x, g).clone()
+    t.to(torch.float32)                       # parameters become fp32 (same values): same packed bf16 weights
+    assert t._packed is None
+    assert torch.equal(t(x, g), ref)
+    with torch.no_grad():
+        t.blocks[0].mlp.down_proj.bias.add_(1.0)
+    t.to(DEV)                                 # any _apply invalidates the pack: the edit becomes visible
+    assert not torch.equal(t(x, g), ref)
