@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200VIT_VERSION 2
+#define B200VIT_VERSION 3
 
 enum {
   B200VIT_OK = 0,
@@ -56,7 +56,11 @@ typedef struct b200vit_cfg {
  * (HF modeling :411-451, :512), cu_seqlens (:488-496), cu_window_seqlens
  * (:476), rope cos/sin tables in window order (:382-409, :485-486), attention
  * work lists, workspace layout.  Host part is computed at create time (no GPU
- * needed); device copies are uploaded lazily by the first forward.           */
+ * needed); device copies are uploaded lazily by the first forward (to the device
+ * current at that moment: one plan per device).  After that a plan is immutable
+ * and may be shared by any number of threads and streams: b200vit_forward takes
+ * it const, and everything a call mutates lives in the caller's workspace (the
+ * host-side memo of tensor maps per workspace is internal and locked).        */
 typedef struct b200vit_plan b200vit_plan;
 
 int b200vit_version(void);
@@ -75,7 +79,8 @@ enum {
   B200VIT_PLAN_ROPE_COS = 6,       /* fp32  [M,head_dim/2] window order                  */
   B200VIT_PLAN_ROPE_SIN = 7,       /* fp32  [M,head_dim/2] window order                  */
   B200VIT_PLAN_POS_IDS = 8,        /* int32 [M,2] (hpos,wpos), ORIGINAL patch order       */
-  B200VIT_PLAN_ROPE_PACKED = 9     /* fp16x2 [M,head_dim/2] (cos,sin) pairs as the QKV epilogue reads them */
+  B200VIT_PLAN_ROPE_TABLE = 9,     /* fp32 [P,head_dim/4,2] (cos,sin) by coordinate, P = largest grid side: what the QKV epilogue reads */
+  B200VIT_PLAN_ROPE_POS = 10       /* int32 [M,2] (hpos,wpos), WINDOW order: the row positions the QKV epilogue reads   */
 };
 /* Copies a host-side plan array into h_dst (cap bytes).  Returns the number of
  * bytes the array holds (so a call with cap = 0 sizes it), negative on error.  */
@@ -83,17 +88,19 @@ int64_t b200vit_plan_get(const b200vit_plan* plan, int which, void* h_dst, size_
 size_t b200vit_workspace_bytes(const b200vit_plan* plan);
 
 /* ------------------------------------------------------------------ weights
- * Packed once by the host module (rga3-release_b200/module.py::pack_weights)
- * from the HF state_dict; all bf16 matrices are [N, K] row-major (nn.Linear
- * layout), K padded as noted.                                                */
+ * Packed once from the HF state_dict by b200vit_pack_weights (below); all bf16
+ * matrices are [N, K] row-major (nn.Linear layout), K padded as noted.  The
+ * per-block RMSNorms (HF modeling :57-71, :313-320) do not exist as kernels:
+ * RMSNorm(x) W^T == rstd(x) * (x (W diag(gamma))^T), so gamma is folded into the
+ * columns of the following weight matrix and rstd is applied per row in that
+ * GEMM's epilogue (SURVEY.md 2.1 "RMSNorm x65").                               */
 typedef struct b200vit_layer_weights {
-  const float* norm1_w;     /* [D]                                                      */
-  const void* qkv_w;        /* bf16 [3D, D]                                             */
+  const void* qkv_w;        /* bf16 [3D, D], column k scaled by norm1.weight[k]          */
   const float* qkv_b;       /* [3D]                                                     */
   const void* proj_w;       /* bf16 [D, D]                                              */
   const float* proj_b;      /* [D]                                                      */
-  const float* norm2_w;     /* [D]                                                      */
-  const void* gateup_w;     /* bf16 [2*Ipad, D], rows interleaved g0,u0,g1,u1,...        */
+  const void* gateup_w;     /* bf16 [2*Ipad, D], rows interleaved g0,u0,g1,u1,...,       */
+                            /* column k scaled by norm2.weight[k]                        */
   const float* gateup_b;    /* [2*Ipad] interleaved the same way                         */
   const void* down_w;       /* bf16 [D, Ipad] (zero columns beyond I)                    */
   const float* down_b;      /* [D]                                                      */
@@ -102,13 +109,37 @@ typedef struct b200vit_layer_weights {
 typedef struct b200vit_weights {
   const void* patch_w;      /* bf16 [D, C*tp*p*p] (Conv3d weight viewed 2-D, HF :106-114) */
   const b200vit_layer_weights* layers; /* HOST array [depth] of device pointers          */
-  const float* merger_ln_w; /* [D]                                                      */
+  const float* merger_ln_w; /* [D]  (the merger's ln_q stays a kernel: its output is viewed [M/4, 4D]) */
   const void* merger_fc1_w; /* bf16 [4D, 4D]                                            */
   const float* merger_fc1_b;
   const void* merger_fc2_w; /* bf16 [out_hidden, 4D]                                    */
   const float* merger_fc2_b;
   int32_t ipad;             /* padded intermediate size (multiple of 128)               */
 } b200vit_weights;
+
+/* The tower's parameters as the HF state_dict holds them (names in SURVEY.md 8b):
+ * every tensor row-major contiguous, all of one element type, HOST or DEVICE
+ * pointers (detected per pointer).                                            */
+typedef struct b200vit_raw_layer {
+  const void *norm1_w, *qkv_w, *qkv_b, *proj_w, *proj_b;            /* [D] [3D,D] [3D] [D,D] [D] */
+  const void *norm2_w, *gate_w, *gate_b, *up_w, *up_b, *down_w, *down_b; /* [D] [I,D] [I] [I,D] [I] [D,I] [D] */
+} b200vit_raw_layer;
+typedef struct b200vit_raw_weights {
+  int32_t dtype;                       /* 0 fp32, 1 fp16, 2 bf16                         */
+  const void* patch_w;                 /* [D, C, tp, p, p]                               */
+  const b200vit_raw_layer* layers;     /* HOST array [depth]                             */
+  const void *merger_ln_w, *merger_fc1_w, *merger_fc1_b, *merger_fc2_w, *merger_fc2_b;
+} b200vit_raw_weights;
+
+/* Packs the raw parameters into one caller-owned DEVICE buffer (256-byte aligned,
+ * b200vit_packed_weights_bytes(cfg) bytes) and fills `out` / `out_layers`
+ * (HOST array [depth]; out->layers points at it) with pointers into that buffer:
+ * bf16 casts, gamma fold of norm1/norm2 into qkv/gate/up, gate/up row interleave,
+ * I -> Ipad zero padding.  Work is enqueued on `stream`; host-resident inputs are
+ * staged synchronously.                                                        */
+size_t b200vit_packed_weights_bytes(const b200vit_cfg* cfg);
+int b200vit_pack_weights(const b200vit_cfg* cfg, const b200vit_raw_weights* raw, void* d_packed, size_t packed_bytes,
+                         b200vit_weights* out, b200vit_layer_weights* out_layers, b200vit_stream stream);
 
 /* ------------------------------------------------------------------ overlay
  * Output of the STOM policy (/root/reference/model/STOM.py:72-141), which stays
@@ -148,9 +179,17 @@ typedef struct b200vit_frames {
  * (out_f32 = 0) or fp32, in ORIGINAL merged-token order.  d_last_hidden
  * (optional, may be NULL): fp32 [M, D] in window order (HF 5.x
  * last_hidden_state).                                                         */
-int b200vit_forward(b200vit_plan* plan, const b200vit_weights* w, const void* d_pixel_values,
+int b200vit_forward(const b200vit_plan* plan, const b200vit_weights* w, const void* d_pixel_values,
                     const b200vit_frames* frames, const b200vit_overlay* overlay, void* d_out, int out_f32,
                     float* d_last_hidden, void* d_workspace, size_t workspace_bytes, b200vit_stream stream);
+
+/* The forward keeps the fp32 residual stream resident in L2 (a persisting access-policy window on the caller's
+ * stream for the duration of the call) when it fits.  That needs the DEVICE-wide limit
+ * cudaLimitPersistingL2CacheSize, which the library grows (never shrinks) to the largest residual stream seen and
+ * gives back only for a clip whose stream does not fit (long videos run faster with the whole L2 as normal cache).
+ * mode 0: never touch the limit (a host application that manages it itself); mode 1 (default): as described.
+ * The environment variable B200VIT_L2_PERSIST=0 selects mode 0 at first use.                                    */
+int b200vit_set_l2_persist(int mode);
 
 /* Number of kernel launches one b200vit_forward enqueues for this plan.       */
 int b200vit_forward_launches(const b200vit_plan* plan, int with_frames);
@@ -211,19 +250,36 @@ enum {
   B200VIT_EPI_SWIGLU = 3,        /* bf16 out[:, c/2] = silu(acc[c]+b[c]) * (acc[c+1]+b[c+1])   */
   B200VIT_EPI_BIAS_GELU = 4,     /* bf16 out = gelu_erf(acc + bias)                           */
   B200VIT_EPI_BIAS_BF16 = 5,     /* bf16 out[row_map[r]] = acc + bias                         */
-  B200VIT_EPI_BIAS_F32 = 6       /* f32  out[row_map[r]] = acc + bias                         */
+  B200VIT_EPI_BIAS_F32 = 6,      /* f32  out[row_map[r]] = acc + bias                         */
+  B200VIT_EPI_BIAS_RESIDUAL_NORM = 7 /* out_f32 += acc + bias, and from the NEW out: d_out_bf16 = bf16(out),
+                                    d_rowsq_out partial row sums of out^2 (feeds the next fused RMSNorm) */
 };
+/* int32 words of the d_sync scratch (zeroed once; every launch leaves it zeroed) */
+#define B200VIT_GEMM_SYNC_INTS 4096
 typedef struct b200vit_gemm_args {
   const void* d_a;      /* bf16 [M, K] row-major, lda = K                              */
   const void* d_b;      /* bf16 [N, K] row-major (nn.Linear weight)                    */
   void* d_out;          /* see epilogue                                               */
   const float* d_bias;  /* [N] or NULL                                                */
   const int32_t* d_row_map; /* [M] or NULL (identity)                                  */
-  const void* d_rope;   /* QKV_ROPE: [M, 40] fp16 pairs (cos, sin), 4 bytes per entry, window order */
+  const void* d_rope;   /* QKV_ROPE: fp32 [P, 20, 2]: (cos, sin) of coordinate * inv_freq[k] for coordinates 0..P-1 --
+                           HF's own rotary table before the pos_ids gather (modeling :117-130, :382-409)          */
+  const int32_t* d_rope_pos; /* QKV_ROPE: int32 [M, 2] (hpos, wpos) of every A row: head dims 0..19 (and 40..59) turn
+                           with hpos, 20..39 (and 60..79) with wpos                                               */
   int32_t m, n, k;
   int32_t ldo;          /* leading dimension of out, in elements                       */
   int32_t rope_cols;    /* QKV_ROPE: columns [0, rope_cols) are rotated (= 2D)         */
   int32_t epilogue;     /* B200VIT_EPI_*                                              */
+  /* fused RMSNorm (all optional, NULL/0 = off) */
+  void* d_out_bf16;        /* STORE_F32 (optional), BIAS_RESIDUAL_NORM (required): bf16 copy of the fp32 output,
+                              same rows (row_map applied) and leading dimension as d_out                      */
+  float* d_rowsq_out;      /* same epilogues: [ceil(N/128)][M] per-row sums of out^2 over each 128-column group */
+  const float* d_rowsq_in; /* QKV_ROPE, SWIGLU: [rowsq_parts][M] partial sums of squares of the fp32 rows A was
+                              cast from; the accumulator row is scaled by rsqrt(sum / K + norm_eps) before the bias */
+  int32_t rowsq_parts;
+  float norm_eps;
+  int32_t* d_sync;         /* BIAS_RESIDUAL_NORM: zeroed int32[B200VIT_GEMM_SYNC_INTS]; enables the balanced
+                              (stream-K) decomposition with a fixed, bit-reproducible addition order; NULL = whole tiles */
 } b200vit_gemm_args;
 /* out = epilogue(A[M,K] * B[N,K]^T): tcgen05/TMEM GEMM fed by TMA.             */
 int b200vit_gemm(const b200vit_gemm_args* args, b200vit_stream stream);

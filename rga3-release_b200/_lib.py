@@ -10,14 +10,17 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200vit.so")
+LIB_PATH = os.environ.get("B200VIT_LIB") or os.path.join(HERE, "libb200vit.so")  # B200VIT_LIB: experiment builds only
 
 # epilogues / enums (keep in sync with include/b200vit.h)
-EPI_STORE_F32, EPI_QKV_ROPE, EPI_BIAS_RESIDUAL, EPI_SWIGLU, EPI_BIAS_GELU, EPI_BIAS_BF16, EPI_BIAS_F32 = range(7)
+(EPI_STORE_F32, EPI_QKV_ROPE, EPI_BIAS_RESIDUAL, EPI_SWIGLU, EPI_BIAS_GELU, EPI_BIAS_BF16, EPI_BIAS_F32,
+ EPI_BIAS_RESIDUAL_NORM) = range(8)
+GEMM_SYNC_INTS = 4096
+VERSION = 3
 LAYER_NONE, LAYER_RGBA, LAYER_PALETTE, LAYER_BOX = range(4)
 FRAME_NONE, FRAME_LAYER, FRAME_CIRCLE = range(3)
 (PLAN_M, PLAN_WINDOW_INDEX, PLAN_REVERSE_INDEX, PLAN_CU_WINDOW, PLAN_CU_FULL, PLAN_ROW_MAP, PLAN_ROPE_COS,
- PLAN_ROPE_SIN, PLAN_POS_IDS, PLAN_ROPE_PACKED) = range(10)
+ PLAN_ROPE_SIN, PLAN_POS_IDS, PLAN_ROPE_TABLE, PLAN_ROPE_POS) = range(11)
 
 
 class Cfg(C.Structure):
@@ -27,8 +30,18 @@ class Cfg(C.Structure):
 
 
 class LayerWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("norm1_w", "qkv_w", "qkv_b", "proj_w", "proj_b", "norm2_w", "gateup_w",
-                                          "gateup_b", "down_w", "down_b")]
+    _fields_ = [(n, C.c_void_p) for n in ("qkv_w", "qkv_b", "proj_w", "proj_b", "gateup_w", "gateup_b", "down_w", "down_b")]
+
+
+class RawLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("norm1_w", "qkv_w", "qkv_b", "proj_w", "proj_b", "norm2_w", "gate_w", "gate_b",
+                                          "up_w", "up_b", "down_w", "down_b")]
+
+
+class RawWeights(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("patch_w", C.c_void_p), ("layers", C.POINTER(RawLayer)),
+                ("merger_ln_w", C.c_void_p), ("merger_fc1_w", C.c_void_p), ("merger_fc1_b", C.c_void_p),
+                ("merger_fc2_w", C.c_void_p), ("merger_fc2_b", C.c_void_p)]
 
 
 class Weights(C.Structure):
@@ -54,9 +67,10 @@ class Frames(C.Structure):
 
 class GemmArgs(C.Structure):
     _fields_ = [("d_a", C.c_void_p), ("d_b", C.c_void_p), ("d_out", C.c_void_p), ("d_bias", C.c_void_p),
-                ("d_row_map", C.c_void_p), ("d_rope", C.c_void_p), ("m", C.c_int32),
+                ("d_row_map", C.c_void_p), ("d_rope", C.c_void_p), ("d_rope_pos", C.c_void_p), ("m", C.c_int32),
                 ("n", C.c_int32), ("k", C.c_int32), ("ldo", C.c_int32), ("rope_cols", C.c_int32),
-                ("epilogue", C.c_int32)]
+                ("epilogue", C.c_int32), ("d_out_bf16", C.c_void_p), ("d_rowsq_out", C.c_void_p),
+                ("d_rowsq_in", C.c_void_p), ("rowsq_parts", C.c_int32), ("norm_eps", C.c_float), ("d_sync", C.c_void_p)]
 
 
 EXPORTS = {
@@ -69,6 +83,10 @@ EXPORTS = {
     "b200vit_forward": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p, C.POINTER(Frames), C.POINTER(Overlay),
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200vit_forward_launches": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200vit_set_l2_persist": (C.c_int, [C.c_int]),
+    "b200vit_packed_weights_bytes": (C.c_size_t, [C.POINTER(Cfg)]),
+    "b200vit_pack_weights": (C.c_int, [C.POINTER(Cfg), C.POINTER(RawWeights), C.c_void_p, C.c_size_t, C.POINTER(Weights),
+                                       C.POINTER(LayerWeights), C.c_void_p]),
     "b200vit_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "b200vit_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "b200vit_overlay_composite": (C.c_int, [C.POINTER(Frames), C.POINTER(Overlay), C.c_void_p, C.c_void_p]),

@@ -9,8 +9,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libb200vit.so")
-SOURCES = ["common.cu", "gemm.cu", "attention_tc.cu", "elementwise.cu", "overlay.cu", "stom_policy.cu", "resize.cu", "api.cu"]
+# B200VIT_BUILD_TAG=<tag> builds an experiment variant next to the product library (libb200vit_<tag>.so, own object
+# directory) -- e.g. with B200VIT_NVCC_EXTRA=-DB200_GEMM_TIMING; _lib.py loads it when B200VIT_LIB names it.
+TAG = os.environ.get("B200VIT_BUILD_TAG", "")
+LIB = os.path.join(HERE, f"libb200vit_{TAG}.so" if TAG else "libb200vit.so")
+SOURCES = ["common.cu", "gemm.cu", "attention_tc.cu", "elementwise.cu", "overlay.cu", "stom_policy.cu", "resize.cu", "pack.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"] + os.environ.get("B200VIT_NVCC_EXTRA", "").split()
 
@@ -31,7 +34,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, f"build_{TAG}" if TAG else "build")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "b200vit.h"))

@@ -10,7 +10,25 @@
 #include <new>
 #include <vector>
 
+#include <list>
+#include <memory>
+
 #include "internal.h"
+
+namespace b200 {
+struct CallCache {
+  void* workspace = nullptr;
+  std::vector<GemmPrepared> gemm;   // one memo per GEMM call site of forward()
+  AttnPrepared attn;
+  // optional per-launch profiling (cudaEvent pairs around every launch of a forward)
+  std::vector<cudaEvent_t> ev;      // 2 per launch
+  std::vector<int> ev_kind;         // B200VIT_K_* per launch
+  size_t ev_used = 0;
+  ~CallCache() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+}  // namespace b200
 
 using namespace b200;
 
@@ -24,30 +42,32 @@ struct b200vit_plan {
   std::vector<int64_t> window_index, reverse_index;
   std::vector<int32_t> cu_window, cu_full, row_map, merge_map, pos_ids;
   std::vector<float> rope_cos, rope_sin;  // [M, head_dim/2] in window order
-  std::vector<uint32_t> rope_packed;      // same table as fp16 (cos, sin) pairs -- what the QKV epilogue reads
+  std::vector<float2> rope_table;         // [P, head_dim/4] fp32 (cos, sin) of coordinate * inv_freq: what the QKV epilogue reads
+  std::vector<int32_t> rope_pos;          // [M, 2] (hpos, wpos) in window order
   std::vector<AttnTile> tiles_window, tiles_full;         // tcgen05 attention
   std::vector<int32_t> bounds_window, bounds_full;        // per-row [lo, hi) of the row's segment
   int maxblk_window = 0, maxblk_full = 0;
-  AttnPrepared attn_cache;
   // workspace layout (byte offsets)
-  size_t off_x = 0, off_h = 0, off_qkv = 0, off_attn = 0, off_act = 0, off_pv = 0, ws_bytes = 0;
-  int ipad = 0, kpe = 0;
-  // device copies (lazy)
-  std::mutex mu, fwd_mu;
-  bool uploaded = false;
-  int32_t* d_row_map = nullptr;
-  int32_t* d_merge_map = nullptr;
-  uint32_t* d_rope = nullptr;
-  AttnTile* d_tiles_window = nullptr;
-  AttnTile* d_tiles_full = nullptr;
-  int32_t* d_bounds_window = nullptr;
-  int32_t* d_bounds_full = nullptr;
-  std::vector<GemmPrepared> gemm_cache;   // one memo per GEMM call site of forward()
-  // optional per-launch profiling (cudaEvent pairs around every launch of a forward)
-  bool profile = false;
-  std::vector<cudaEvent_t> ev;       // 2 per launch
-  std::vector<int> ev_kind;          // B200VIT_K_* per launch
-  size_t ev_used = 0;
+  size_t off_x = 0, off_h = 0, off_qkv = 0, off_attn = 0, off_act = 0, off_pv = 0, off_rowsq = 0, off_sync = 0, ws_bytes = 0;
+  int ipad = 0, kpe = 0, rowsq_parts = 0;
+  // device copies (lazy, then immutable: a plan is shared freely between threads and streams)
+  mutable std::mutex mu;
+  mutable bool uploaded = false;
+  mutable int device = -1;
+  mutable int32_t* d_row_map = nullptr;
+  mutable int32_t* d_merge_map = nullptr;
+  mutable float2* d_rope = nullptr;
+  mutable int32_t* d_rope_pos = nullptr;
+  mutable AttnTile* d_tiles_window = nullptr;
+  mutable AttnTile* d_tiles_full = nullptr;
+  mutable int32_t* d_bounds_window = nullptr;
+  mutable int32_t* d_bounds_full = nullptr;
+  // Host-side memos of one forward (tensor maps, launch geometry, profiling events) depend on the workspace and
+  // weight pointers, not on the plan: one CallCache per workspace, looked up under `mu`, then used lock-free by the
+  // calling thread (two concurrent forwards on the SAME workspace would race on the activations anyway).
+  mutable std::list<std::unique_ptr<b200::CallCache>> caches;
+  mutable b200::CallCache* last_cache = nullptr;
+  mutable bool profile = false;
 };
 
 namespace {
@@ -120,10 +140,19 @@ void build_rope(b200vit_plan& p) {
               }
             }
   }
-  p.rope_packed.resize(p.rope_cos.size());
-  for (size_t i = 0; i < p.rope_cos.size(); ++i) {
-    const __half2 h = __floats2half2_rn(p.rope_cos[i], p.rope_sin[i]);
-    std::memcpy(&p.rope_packed[i], &h, 4);
+  // the same values by coordinate (HF builds exactly this table, then gathers it with pos_ids, :396-408)
+  int64_t side = 1;
+  for (size_t gi = 0; gi < p.grid.size() / 3; ++gi) side = std::max(side, std::max(p.grid[gi * 3 + 1], p.grid[gi * 3 + 2]));
+  p.rope_table.resize(side * nfreq);
+  for (int64_t c0 = 0; c0 < side; ++c0)
+    for (int k = 0; k < nfreq; ++k) {
+      const float a = static_cast<float>(c0) * inv_freq[k];
+      p.rope_table[c0 * nfreq + k] = make_float2(cosf(a), sinf(a));
+    }
+  p.rope_pos.resize(p.m * 2);
+  for (int64_t r0 = 0; r0 < p.m; ++r0) {
+    p.rope_pos[p.row_map[r0] * 2] = p.pos_ids[r0 * 2];
+    p.rope_pos[p.row_map[r0] * 2 + 1] = p.pos_ids[r0 * 2 + 1];
   }
 }
 
@@ -135,13 +164,20 @@ int upload(T** dst, const std::vector<T>& src) {
   return 0;
 }
 
-int ensure_uploaded(b200vit_plan* p) {
+int ensure_uploaded(const b200vit_plan* p) {
   std::lock_guard<std::mutex> lock(p->mu);
-  if (p->uploaded) return 0;
+  int dev = 0;
+  B200_CUDA_OK(cudaGetDevice(&dev));
+  if (p->uploaded) {
+    if (dev != p->device) return fail(B200VIT_EINVAL, "forward: this plan's tables live on another device (one plan per device)");
+    return 0;
+  }
   int rc;
+  p->device = dev;
   if ((rc = upload(&p->d_row_map, p->row_map))) return rc;
   if ((rc = upload(&p->d_merge_map, p->merge_map))) return rc;
-  if ((rc = upload(&p->d_rope, p->rope_packed))) return rc;
+  if ((rc = upload(&p->d_rope, p->rope_table))) return rc;
+  if ((rc = upload(&p->d_rope_pos, p->rope_pos))) return rc;
   if ((rc = upload(&p->d_tiles_window, p->tiles_window))) return rc;
   if ((rc = upload(&p->d_tiles_full, p->tiles_full))) return rc;
   if ((rc = upload(&p->d_bounds_window, p->bounds_window))) return rc;
@@ -152,10 +188,11 @@ int ensure_uploaded(b200vit_plan* p) {
 
 // Records an event pair around one launch when profiling is on.
 struct Prof {
-  b200vit_plan* p;
+  CallCache* p;
   cudaStream_t st;
+  bool on;
   void begin(int kind) {
-    if (!p->profile) return;
+    if (!on) return;
     if (p->ev_used + 2 > p->ev.size()) {
       for (int i = 0; i < 2; ++i) {
         cudaEvent_t e;
@@ -169,7 +206,7 @@ struct Prof {
     cudaEventRecord(p->ev[p->ev_used], st);
   }
   void end() {
-    if (!p->profile) return;
+    if (!on) return;
     cudaEventRecord(p->ev[p->ev_used + 1], st);
     p->ev_used += 2;
   }
@@ -179,49 +216,67 @@ struct Prof {
 // x is read by both RMSNorms and read-modify-written by both residual GEMMs of every block (SURVEY.md 8d:
 // 252 MB of HBM traffic per block otherwise).  Implemented as a persisting access-policy window on the
 // caller's stream for the duration of the forward.  B200VIT_L2_PERSIST=0 disables it.
+// Policy (b200vit_set_l2_persist): 0 = never touch the device's persisting-L2 limit, 1 (default) = manage it.
+// The limit is a per-DEVICE setting shared with the host application, so it is changed rarely and under a lock:
+// grown (never shrunk) to the largest residual stream that fits, and given back only when a clip arrives whose
+// residual stream does not fit at all.
+struct L2State {
+  bool probed = false;
+  size_t max_persist = 0, max_window = 0, set_aside = 0;
+};
+std::mutex g_l2_mu;
+L2State g_l2[64];
+int g_l2_mode = -1;
+
 struct L2Persist {
   cudaStream_t stream;
   bool active = false;
   L2Persist(cudaStream_t st, void* base, size_t bytes) : stream(st) {
-    static int enabled = -1;
-    static size_t max_persist = 0, max_window = 0;
-    if (enabled < 0) {
-      const char* e = getenv("B200VIT_L2_PERSIST");
-      enabled = (e == nullptr || e[0] != '0') ? 1 : 0;
-      int dev = 0, v = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev);
-      max_persist = static_cast<size_t>(v);
-      cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-      max_window = static_cast<size_t>(v);
-      if (!(enabled && max_persist > 0)) enabled = 0;
-      cudaGetLastError();
-    }
-    static size_t set_aside = 0;  // carve out only what the residual stream needs: the rest stays normal L2
-    if (!enabled || bytes == 0) return;
-    if (bytes > max_persist || bytes > max_window) {
-      // long clips: the residual stream does not fit the persisting partition; a partial window only shrinks the
-      // normal L2 (measured on cfg 4) -- give the carve-out back and stream
-      if (set_aside != 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) == cudaSuccess) set_aside = 0;
-      cudaGetLastError();
-      return;
-    }
-    const size_t want = bytes;
-    if (want != set_aside) {
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || bytes == 0) return;
+    size_t max_window = 0, max_persist = 0;
+    {
+      std::lock_guard<std::mutex> lock(g_l2_mu);
+      if (g_l2_mode < 0) {
+        const char* e = getenv("B200VIT_L2_PERSIST");
+        g_l2_mode = (e == nullptr || e[0] != '0') ? 1 : 0;
+      }
+      if (g_l2_mode == 0) return;
+      L2State& s = g_l2[dev];
+      if (!s.probed) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        s.max_persist = static_cast<size_t>(v > 0 ? v : 0);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        s.max_window = static_cast<size_t>(v > 0 ? v : 0);
+        s.probed = true;
+        cudaGetLastError();
+      }
+      if (s.max_persist == 0) return;
+      if (bytes > s.max_persist || bytes > s.max_window) {
+        // long clips: the residual stream does not fit the persisting partition; a partial window only shrinks the
+        // normal L2 (measured on cfg 4) -- give the carve-out back and stream
+        if (s.set_aside != 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) == cudaSuccess) s.set_aside = 0;
         cudaGetLastError();
         return;
       }
-      set_aside = want;
+      if (bytes > s.set_aside) {
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) {
+          cudaGetLastError();
+          return;
+        }
+        s.set_aside = bytes;
+      }
+      max_window = s.max_window, max_persist = s.max_persist;
     }
     cudaStreamAttrValue attr;
     std::memset(&attr, 0, sizeof(attr));
-    const size_t win = bytes < max_window ? bytes : max_window;
     attr.accessPolicyWindow.base_ptr = base;
-    attr.accessPolicyWindow.num_bytes = win;
-    attr.accessPolicyWindow.hitRatio = win <= max_persist ? 1.0f : static_cast<float>(max_persist) / static_cast<float>(win);
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    (void)max_window, (void)max_persist;
     active = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
     cudaGetLastError();
   }
@@ -302,6 +357,9 @@ int b200vit_plan_create(const int64_t* h_grid_thw, int n_grids, const b200vit_cf
   p->off_attn = off, off = align_up(off + M * D * 2, 1024);
   p->off_act = off, off = align_up(off + M * p->ipad * 2, 1024);
   p->off_pv = off, off = align_up(off + M * p->kpe * 2, 1024);
+  p->rowsq_parts = (c.hidden + 127) / 128;
+  p->off_rowsq = off, off = align_up(off + M * p->rowsq_parts * 4, 1024);
+  p->off_sync = off, off = align_up(off + B200VIT_GEMM_SYNC_INTS * 4, 1024);
   p->ws_bytes = off;
   *out = p;
   return 0;
@@ -312,11 +370,11 @@ void b200vit_plan_destroy(b200vit_plan* p) {
   cudaFree(p->d_row_map);
   cudaFree(p->d_merge_map);
   cudaFree(p->d_rope);
+  cudaFree(p->d_rope_pos);
   cudaFree(p->d_tiles_window);
   cudaFree(p->d_tiles_full);
   cudaFree(p->d_bounds_window);
   cudaFree(p->d_bounds_full);
-  for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
   delete p;
 }
 
@@ -334,7 +392,8 @@ int64_t b200vit_plan_get(const b200vit_plan* p, int which, void* h_dst, size_t c
     case B200VIT_PLAN_ROPE_COS: src = p->rope_cos.data(), bytes = p->rope_cos.size() * 4; break;
     case B200VIT_PLAN_ROPE_SIN: src = p->rope_sin.data(), bytes = p->rope_sin.size() * 4; break;
     case B200VIT_PLAN_POS_IDS: src = p->pos_ids.data(), bytes = p->pos_ids.size() * 4; break;
-    case B200VIT_PLAN_ROPE_PACKED: src = p->rope_packed.data(), bytes = p->rope_packed.size() * 4; break;
+    case B200VIT_PLAN_ROPE_TABLE: src = p->rope_table.data(), bytes = p->rope_table.size() * 8; break;
+    case B200VIT_PLAN_ROPE_POS: src = p->rope_pos.data(), bytes = p->rope_pos.size() * 4; break;
     default: return fail(B200VIT_EINVAL, "plan_get: unknown array id");
   }
   if (h_dst && cap >= bytes) std::memcpy(h_dst, src, bytes);
@@ -346,10 +405,28 @@ size_t b200vit_workspace_bytes(const b200vit_plan* p) { return p ? p->ws_bytes :
 int b200vit_forward_launches(const b200vit_plan* p, int with_frames) {
   if (!p) return 0;
   const int t_pad_windows = 1;  // one overlay/patchify launch per 128 frames; clips here are <= 128 frames
-  return (with_frames ? t_pad_windows : 0) + 1 + p->cfg.depth * 7 + 3;
+  return (with_frames ? t_pad_windows : 0) + 1 + p->cfg.depth * 5 + 3;
 }
 
-int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pixel_values, const b200vit_frames* frames,
+// The per-workspace memo of this plan (created on first use; at most 8 kept, oldest dropped first).
+static CallCache* call_cache(const b200vit_plan* p, void* workspace, size_t gemm_sites) {
+  std::lock_guard<std::mutex> lock(p->mu);
+  for (auto it = p->caches.begin(); it != p->caches.end(); ++it)
+    if ((*it)->workspace == workspace) {
+      if (it != p->caches.begin()) p->caches.splice(p->caches.begin(), p->caches, it);
+      p->last_cache = p->caches.front().get();
+      return p->last_cache;
+    }
+  if (p->caches.size() >= 8) p->caches.pop_back();
+  p->caches.emplace_front(new CallCache());
+  CallCache* c = p->caches.front().get();
+  c->workspace = workspace;
+  c->gemm.assign(gemm_sites, GemmPrepared());
+  p->last_cache = c;
+  return c;
+}
+
+int b200vit_forward(const b200vit_plan* p, const b200vit_weights* w, const void* d_pixel_values, const b200vit_frames* frames,
                     const b200vit_overlay* overlay, void* d_out, int out_f32, float* d_last_hidden, void* d_workspace,
                     size_t workspace_bytes, b200vit_stream stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -365,19 +442,23 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
   if (w->ipad != p->ipad) return fail(B200VIT_EINVAL, "forward: weights packed with a different intermediate padding");
   const int M = static_cast<int>(p->m), D = c.hidden;
   uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
-  float* x = reinterpret_cast<float*>(ws + p->off_x);
-  void* h = ws + p->off_h;
+  float* x = reinterpret_cast<float*>(ws + p->off_x);          // fp32 residual stream, window order
+  void* xb = ws + p->off_h;                                    // its bf16 copy = A operand of the QKV / gate-up GEMMs
   void* qkv = ws + p->off_qkv;
   void* attn = ws + p->off_attn;
   void* act = ws + p->off_act;
   void* pv = ws + p->off_pv;
+  float* rowsq = reinterpret_cast<float*>(ws + p->off_rowsq);  // [parts][M] partial row sums of x^2
+  int32_t* sync = reinterpret_cast<int32_t*>(ws + p->off_sync);
 
-  std::lock_guard<std::mutex> fwd_lock(p->fwd_mu);   // call-site memos and event lists are per plan
-  if (p->gemm_cache.size() != static_cast<size_t>(3 + 4 * c.depth)) p->gemm_cache.assign(3 + 4 * c.depth, GemmPrepared());
+  CallCache* cc = call_cache(p, d_workspace, static_cast<size_t>(3 + 4 * c.depth));
   int site = 0;
-  Prof prof{p, stream};
-  p->ev_used = 0;
+  Prof prof{cc, stream, p->profile};
+  cc->ev_used = 0;
   L2Persist keep_x(stream, x, static_cast<size_t>(M) * D * 4);
+  // stream-K hand-over flags: every launch leaves them zeroed, but the workspace is the caller's (first use, or a
+  // forward that failed half-way)
+  B200_CUDA_OK(cudaMemsetAsync(sync, 0, B200VIT_GEMM_SYNC_INTS * 4, stream));
   const void* a0 = d_pixel_values;
   if (frames) {
     if (p->grid.size() != 3) return fail(B200VIT_EINVAL, "forward: the frames entry takes a single-clip plan");
@@ -391,93 +472,101 @@ int b200vit_forward(b200vit_plan* p, const b200vit_weights* w, const void* d_pix
     a0 = pv;
   }
   b200vit_gemm_args g;
+  auto gemm = [&](int kind) {
+    prof.begin(kind);
+    const int r = launch_gemm(g, stream, &cc->gemm[site++]);
+    prof.end();
+    return r;
+  };
+  // patch embed (+ window reorder in the store); also the first RMSNorm's inputs: bf16(x) and the row sums of x^2
   std::memset(&g, 0, sizeof(g));
-  // patch embed (+ window reorder in the store)
   g.d_a = a0, g.d_b = w->patch_w, g.d_out = x, g.d_row_map = p->d_row_map;
+  g.d_out_bf16 = xb, g.d_rowsq_out = rowsq;
   g.m = M, g.n = D, g.k = p->kpe, g.ldo = D, g.epilogue = B200VIT_EPI_STORE_F32;
-  prof.begin(B200VIT_K_PATCH_EMBED);
-  if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
-  prof.end();
+  if ((rc = gemm(B200VIT_K_PATCH_EMBED))) return rc;
 
   for (int l = 0; l < c.depth; ++l) {
     const b200vit_layer_weights& lw = w->layers[l];
     const bool full = is_fullatt(c, l);
-    prof.begin(B200VIT_K_RMSNORM);
-    if ((rc = launch_rmsnorm(x, lw.norm1_w, h, M, D, 1e-6f, stream))) return rc;
-    prof.end();
+    // qkv = rope(rstd(x) * (bf16(x) (Wqkv diag(gamma1))^T) + b)          (norm1 + qkv + RoPE, HF :313-316, :231-241)
     std::memset(&g, 0, sizeof(g));
-    g.d_a = h, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_rope = p->d_rope;
+    g.d_a = xb, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_rope = p->d_rope, g.d_rope_pos = p->d_rope_pos;
+    g.d_rowsq_in = rowsq, g.rowsq_parts = p->rowsq_parts, g.norm_eps = 1e-6f;
     g.m = M, g.n = 3 * D, g.k = D, g.ldo = 3 * D, g.rope_cols = 2 * D, g.epilogue = B200VIT_EPI_QKV_ROPE;
-    prof.begin(B200VIT_K_QKV);
-    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
-    prof.end();
+    if ((rc = gemm(B200VIT_K_QKV))) return rc;
     prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
     rc = launch_attention_tc(qkv, attn, full ? p->d_tiles_full : p->d_tiles_window,
                              static_cast<int>(full ? p->tiles_full.size() : p->tiles_window.size()), full ? 256 : 128,
                              full ? p->maxblk_full : p->maxblk_window, full ? p->d_bounds_full : p->d_bounds_window, M,
-                             c.heads, stream, &p->attn_cache);
+                             c.heads, stream, &cc->attn);
     if (rc) return rc;
     prof.end();
+    // x += attn Wp^T + b; xb = bf16(x); rowsq = partial row sums of x^2                            (HF :313-316)
     std::memset(&g, 0, sizeof(g));
     g.d_a = attn, g.d_b = lw.proj_w, g.d_out = x, g.d_bias = lw.proj_b;
-    g.m = M, g.n = D, g.k = D, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
-    prof.begin(B200VIT_K_PROJ);
-    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
-    prof.end();
-    prof.begin(B200VIT_K_RMSNORM);
-    if ((rc = launch_rmsnorm(x, lw.norm2_w, h, M, D, 1e-6f, stream))) return rc;
-    prof.end();
+    g.d_out_bf16 = xb, g.d_rowsq_out = rowsq, g.d_sync = sync;
+    g.m = M, g.n = D, g.k = D, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL_NORM;
+    if ((rc = gemm(B200VIT_K_PROJ))) return rc;
+    // act = silu(g) * u with [g u] = rstd(x) * (bf16(x) (Wgu diag(gamma2))^T) + b            (norm2 + gate/up, HF :88)
     std::memset(&g, 0, sizeof(g));
-    g.d_a = h, g.d_b = lw.gateup_w, g.d_out = act, g.d_bias = lw.gateup_b;
+    g.d_a = xb, g.d_b = lw.gateup_w, g.d_out = act, g.d_bias = lw.gateup_b;
+    g.d_rowsq_in = rowsq, g.rowsq_parts = p->rowsq_parts, g.norm_eps = 1e-6f;
     g.m = M, g.n = 2 * p->ipad, g.k = D, g.ldo = p->ipad, g.epilogue = B200VIT_EPI_SWIGLU;
-    prof.begin(B200VIT_K_GATEUP);
-    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
-    prof.end();
+    if ((rc = gemm(B200VIT_K_GATEUP))) return rc;
     std::memset(&g, 0, sizeof(g));
     g.d_a = act, g.d_b = lw.down_w, g.d_out = x, g.d_bias = lw.down_b;
-    g.m = M, g.n = D, g.k = p->ipad, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL;
-    prof.begin(B200VIT_K_DOWN);
-    if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
-    prof.end();
+    g.d_out_bf16 = xb, g.d_rowsq_out = rowsq, g.d_sync = sync;
+    g.m = M, g.n = D, g.k = p->ipad, g.ldo = D, g.epilogue = B200VIT_EPI_BIAS_RESIDUAL_NORM;
+    if ((rc = gemm(B200VIT_K_DOWN))) return rc;
   }
   if (d_last_hidden)
     B200_CUDA_OK(cudaMemcpyAsync(d_last_hidden, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
-  // merger (HF :133-146) + un-reorder (:512-513)
+  // merger (HF :133-146) + un-reorder (:512-513).  ln_q is the one RMSNorm left as a kernel: its output is viewed
+  // [M/4, 4D], so four different row scales meet inside one K reduction of fc1.
   const int Mm = M / p->unit, Dm = D * p->unit;
   prof.begin(B200VIT_K_RMSNORM);
-  if ((rc = launch_rmsnorm(x, w->merger_ln_w, h, M, D, 1e-6f, stream))) return rc;
+  if ((rc = launch_rmsnorm(x, w->merger_ln_w, xb, M, D, 1e-6f, stream))) return rc;
   prof.end();
   std::memset(&g, 0, sizeof(g));
-  g.d_a = h, g.d_b = w->merger_fc1_w, g.d_out = attn, g.d_bias = w->merger_fc1_b;
+  g.d_a = xb, g.d_b = w->merger_fc1_w, g.d_out = attn, g.d_bias = w->merger_fc1_b;
   g.m = Mm, g.n = Dm, g.k = Dm, g.ldo = Dm, g.epilogue = B200VIT_EPI_BIAS_GELU;
-  prof.begin(B200VIT_K_MERGER_FC1);
-  if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
-  prof.end();
+  if ((rc = gemm(B200VIT_K_MERGER_FC1))) return rc;
   std::memset(&g, 0, sizeof(g));
   g.d_a = attn, g.d_b = w->merger_fc2_w, g.d_out = d_out, g.d_bias = w->merger_fc2_b, g.d_row_map = p->d_merge_map;
   g.m = Mm, g.n = c.out_hidden, g.k = Dm, g.ldo = c.out_hidden;
   g.epilogue = out_f32 ? B200VIT_EPI_BIAS_F32 : B200VIT_EPI_BIAS_BF16;
-  prof.begin(B200VIT_K_MERGER_FC2);
-  if ((rc = launch_gemm(g, stream, &p->gemm_cache[site++]))) return rc;
-  prof.end();
+  if ((rc = gemm(B200VIT_K_MERGER_FC2))) return rc;
+  return 0;
+}
+
+int b200vit_set_l2_persist(int mode) {
+  if (mode != 0 && mode != 1) return fail(B200VIT_EINVAL, "set_l2_persist: mode must be 0 or 1");
+  std::lock_guard<std::mutex> lock(g_l2_mu);
+  g_l2_mode = mode;
   return 0;
 }
 
 int b200vit_profile_enable(b200vit_plan* p, int enable) {
   if (!p) return fail(B200VIT_EINVAL, "profile_enable: null plan");
+  std::lock_guard<std::mutex> lock(p->mu);
   p->profile = enable != 0;
-  p->ev_used = 0;
   return 0;
 }
 
 int b200vit_profile_read(b200vit_plan* p, float* h_ms_by_kind, int32_t* h_count_by_kind) {
   if (!p || !h_ms_by_kind || !h_count_by_kind) return fail(B200VIT_EINVAL, "profile_read: null argument");
   for (int i = 0; i < B200VIT_K_COUNT; ++i) h_ms_by_kind[i] = 0.f, h_count_by_kind[i] = 0;
-  for (size_t i = 0; i + 1 < p->ev_used; i += 2) {
-    B200_CUDA_OK(cudaEventSynchronize(p->ev[i + 1]));
+  CallCache* cc;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    cc = p->last_cache;
+  }
+  if (!cc) return 0;
+  for (size_t i = 0; i + 1 < cc->ev_used; i += 2) {
+    B200_CUDA_OK(cudaEventSynchronize(cc->ev[i + 1]));
     float ms = 0.f;
-    B200_CUDA_OK(cudaEventElapsedTime(&ms, p->ev[i], p->ev[i + 1]));
-    const int k = p->ev_kind[i / 2];
+    B200_CUDA_OK(cudaEventElapsedTime(&ms, cc->ev[i], cc->ev[i + 1]));
+    const int k = cc->ev_kind[i / 2];
     h_ms_by_kind[k] += ms;
     h_count_by_kind[k] += 1;
   }

@@ -933,10 +933,10 @@ int launch_variant(const AttnPrepared& g, const AttnTile* d_tiles, int n_tiles, 
                    float scale_log2, cudaStream_t stream) {
   using L = AttnCfg<QTILES, NKV, NQ, SHARED_KV>;
   auto kern = attn_tc_kernel<QTILES, NKV, NQ, SHARED_KV>;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-    attr = true;
+    attr.mark();
   }
   B200_CUDA_OK(launch_kernel(kern, dim3(n_tiles, heads / hpc), dim3(L::THREADS), L::BYTES, stream, 1, g.tm64, g.tm16, g.to64,
                              g.to16, d_tiles, bd, m_rows, heads, hpc, scale_log2));
@@ -997,10 +997,10 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
     if (!two_threads) return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
     using L = AttnCfg<2, 2, 1, true>;
     constexpr int kSmem = L::BYTES + 4096;  // + partner-exchange area behind the barriers
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.need()) {
       B200_CUDA_OK(cudaFuncSetAttribute(attn_full2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-      attr = true;
+      attr.mark();
     }
     B200_CUDA_OK(launch_kernel(attn_full2_kernel, dim3(n_tiles, heads), dim3(F2_THREADS), kSmem, stream, 1, g.tm64, g.tm16, g.to64,
                                g.to16, d_tiles, bd, m_rows, heads, scale_log2));

@@ -18,6 +18,12 @@
 // Global traffic of the hot epilogues goes through the TMA engine: a thread owns one accumulator
 // ROW, so direct stores would be 32 separate sectors per instruction (measured: the first version
 // of this kernel was epilogue-bound on LSU wavefronts, profiles/r01_*).
+//
+// RMSNorm (HF :57-71, two per block) has no kernel of its own: RMSNorm(x) W^T == rstd(x) * (x (W diag(gamma))^T).
+// gamma is folded into the next weight matrix when the weights are packed (pack.cu); the kernels that WRITE the fp32
+// residual stream (patch embed, proj, down: STORE_F32 / BIAS_RESIDUAL_NORM) also write its bf16 copy -- the next
+// GEMM's A operand -- and per-row partial sums of x^2; the kernels that READ it (QKV_ROPE, SWIGLU) add the partials
+// in index order and scale their accumulator rows by rstd before the bias.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -39,10 +45,38 @@ struct GemmParams {
   void* out;
   const float* bias;
   const int32_t* row_map;
-  const uint32_t* rope;  // [M, 40] half2 (cos, sin)
+  const float2* rope;     // [P, 20] fp32 (cos, sin) of coordinate * inv_freq, P = largest grid side
+  const int2* rope_pos;   // [M] (hpos, wpos) of every row
   int m, n, k, ldo, rope_cols;
-  int stream_k;  // bit 0: stream-K decomposition (BIAS_RESIDUAL only); bit 1: no weight prefetch before the PDL wait
+  int stream_k;  // bit 0: stream-K decomposition (BIAS_RESIDUAL_NORM only); bit 1: no weight prefetch before the PDL wait
+  // fused RMSNorm (HF :57-71): RMSNorm(x) W^T == rstd(x) * (x (W diag(gamma))^T).  Producers of the fp32 residual
+  // stream also emit its bf16 copy (the next GEMM's A operand) and per-row partial sums of x^2, one per 128-column
+  // group, laid out [part][M]; consumers add the partials in index order and scale their accumulator rows by rstd.
+  __nv_bfloat16* out_bf16;
+  float* rowsq_out;
+  const float* rowsq_in;
+  int rowsq_parts;
+  float norm_eps;
+  int32_t* sync;  // stream-K hand-over flags, one per (unit, CTA rank, epilogue warp); zero between launches
 };
+
+// sum of the row's partials in index order (bit-stable) -> rsqrt(mean(x^2) + eps)
+// All loads are issued before the first add (a rolled loop would serialise up to 16 L2 round trips in front of
+// every tile's epilogue); callers ask for it BEFORE they wait for the accumulator.
+constexpr int MAX_ROWSQ_PARTS = 16;
+__device__ __forceinline__ float row_rstd(const GemmParams& p, int row) {
+  if (p.rowsq_in == nullptr) return 1.0f;
+  float v[MAX_ROWSQ_PARTS];
+#pragma unroll
+  for (int i = 0; i < MAX_ROWSQ_PARTS; ++i)
+    v[i] = i < p.rowsq_parts ? __ldg(p.rowsq_in + static_cast<size_t>(i) * p.m + row) : 0.f;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_ROWSQ_PARTS; ++i) s += v[i];
+  return rsqrtf(s / static_cast<float>(p.k) + p.norm_eps);
+}
+
+__host__ __device__ constexpr bool is_resid_norm(int epi) { return epi == B200VIT_EPI_BIAS_RESIDUAL_NORM; }
 
 #ifndef B200_RESID_BUFS
 #define B200_RESID_BUFS 1
@@ -52,6 +86,7 @@ constexpr int RESID_BUFS = B200_RESID_BUFS;  // staging buffers per warp of the 
 __host__ __device__ constexpr int epi_stage_bytes(int epi) {
   return epi == B200VIT_EPI_QKV_ROPE        ? 32 * 160
          : epi == B200VIT_EPI_BIAS_RESIDUAL ? RESID_BUFS * 4096
+         : is_resid_norm(epi) ? 4096  // one 32 x 32 fp32 chunk of (acc + bias) in transit between the two thread layouts
          : epi == B200VIT_EPI_SWIGLU        ? 4096
          : epi == B200VIT_EPI_BIAS_GELU     ? 2 * 4096
                                             : 0;
@@ -90,7 +125,7 @@ __device__ __forceinline__ float4 bias4(const float* bias, int col, int n) {
 // `stg` = this warp's staging buffer (shared address), `row0` = first row of the warp's 32-row slab.
 template <int EPI, int CW>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane, int col0, const GemmParams& p,
-                                              const CUtensorMap* tma_out, uint32_t stg, bool first_split) {
+                                              const CUtensorMap* tma_out, uint32_t stg, bool first_split, float rs) {
   const int row = row0 + lane;
   const bool row_ok = row < p.m;
   if constexpr (EPI == B200VIT_EPI_QKV_ROPE) {
@@ -98,15 +133,24 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
     if (lane == 0) bulk_wait_read<0>();  // previous tile's store has drained the staging buffer
     __syncwarp();
     const uint32_t srow = stg + lane * 160;
+    // `rs` = fused RMSNorm: per-row rstd of the A operand's source
     if (col0 < p.rope_cols) {
-      const uint4* cs = reinterpret_cast<const uint4*>(p.rope + static_cast<size_t>(row_ok ? row : 0) * 40);
+      // HF :382-409: rotary_pos_emb = freqs[pos_ids] with freqs = outer(arange(max_grid), inv_freq): dims 0..19 turn
+      // with the row's hpos, dims 20..39 with its wpos.  The [P, 20] table stays in L1; only 8 bytes per row are new.
+      const int2 pos = row_ok ? __ldg(p.rope_pos + row) : make_int2(0, 0);
+      const float4* th = reinterpret_cast<const float4*>(p.rope + static_cast<size_t>(pos.x) * 20);
+      const float4* tv = reinterpret_cast<const float4*>(p.rope + static_cast<size_t>(pos.y) * 20);
 #pragma unroll
       for (int d0 = 0; d0 < 40; d0 += 8) {
         uint32_t lo[8], hi[8];
         tmem_ld8(taddr + d0, lo);
         tmem_ld8(taddr + 40 + d0, hi);
-        const uint4 t0 = __ldg(cs + (d0 >> 2)), t1 = __ldg(cs + (d0 >> 2) + 1);
-        const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        float4 tw[4];  // (cos, sin) pairs of dims d0 .. d0+7, fp32 as HF rotates (:149-167)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int d = d0 + 2 * i;
+          tw[i] = d < 20 ? __ldg(th + (d >> 1)) : __ldg(tv + ((d - 20) >> 1));
+        }
         float bl[8], bh[8];
         *reinterpret_cast<float4*>(&bl[0]) = ldg4(p.bias + col0 + d0);
         *reinterpret_cast<float4*>(&bl[4]) = ldg4(p.bias + col0 + d0 + 4);
@@ -116,13 +160,12 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
         uint32_t olo[4], ohi[4];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-          const float2 cs0 = __half22float2(*reinterpret_cast<const __half2*>(&tw[j]));      // (cos, sin)
-          const float2 cs1 = __half22float2(*reinterpret_cast<const __half2*>(&tw[j + 1]));
-          const float x0 = __uint_as_float(lo[j]) + bl[j], x1 = __uint_as_float(lo[j + 1]) + bl[j + 1];
-          const float y0 = __uint_as_float(hi[j]) + bh[j], y1 = __uint_as_float(hi[j + 1]) + bh[j + 1];
+          const float c0 = tw[j >> 1].x, s0 = tw[j >> 1].y, c1 = tw[j >> 1].z, s1 = tw[j >> 1].w;
+          const float x0 = __uint_as_float(lo[j]) * rs + bl[j], x1 = __uint_as_float(lo[j + 1]) * rs + bl[j + 1];
+          const float y0 = __uint_as_float(hi[j]) * rs + bh[j], y1 = __uint_as_float(hi[j + 1]) * rs + bh[j + 1];
           // rotate_half: out[d] = x*cos - y*sin ; out[d+40] = y*cos + x*sin   (HF :149-167)
-          olo[j >> 1] = pack_bf16x2(x0 * cs0.x - y0 * cs0.y, x1 * cs1.x - y1 * cs1.y);
-          ohi[j >> 1] = pack_bf16x2(y0 * cs0.x + x0 * cs0.y, y1 * cs1.x + x1 * cs1.y);
+          olo[j >> 1] = pack_bf16x2(x0 * c0 - y0 * s0, x1 * c1 - y1 * s1);
+          ohi[j >> 1] = pack_bf16x2(y0 * c0 + x0 * s0, y1 * c1 + x1 * s1);
         }
         st_shared_v4(srow + d0 * 2, olo[0], olo[1], olo[2], olo[3]);
         st_shared_v4(srow + 80 + d0 * 2, ohi[0], ohi[1], ohi[2], ohi[3]);
@@ -137,8 +180,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const float4 b = ldg4(p.bias + col0 + d0 + j);
-          o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y);
-          o[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
+          o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * rs + b.x, __uint_as_float(v[j + 1]) * rs + b.y);
+          o[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) * rs + b.z, __uint_as_float(v[j + 3]) * rs + b.w);
         }
         st_shared_v4(srow + d0 * 2, o[0], o[1], o[2], o[3]);
         st_shared_v4(srow + d0 * 2 + 16, o[4], o[5], o[6], o[7]);
@@ -195,8 +238,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float g0 = __uint_as_float(v[4 * j]) + b[j].x, u0 = __uint_as_float(v[4 * j + 1]) + b[j].y;
-        const float g1 = __uint_as_float(v[4 * j + 2]) + b[j].z, u1 = __uint_as_float(v[4 * j + 3]) + b[j].w;
+        const float g0 = __uint_as_float(v[4 * j]) * rs + b[j].x, u0 = __uint_as_float(v[4 * j + 1]) * rs + b[j].y;
+        const float g1 = __uint_as_float(v[4 * j + 2]) * rs + b[j].z, u1 = __uint_as_float(v[4 * j + 3]) * rs + b[j].w;
         o[j] = pack_bf16x2(silu_f(g0) * u0, silu_f(g1) * u1);
       }
       st_shared_v4(swz128(stg, lane, (c >> 4)), o[0], o[1], o[2], o[3]);
@@ -242,6 +285,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
     // row-mapped outputs (window reorder of the patch embed, un-reorder of the merger): direct stores
     static_assert(CW % 32 == 0, "generic epilogues work in 32-column chunks");
     const int orow = (row_ok && p.row_map != nullptr) ? p.row_map[row] : row;
+    float ss = 0.f;  // STORE_F32: sum of squares of this thread's CW columns (partial of the next RMSNorm)
 #pragma unroll 1
     for (int c = 0; c < CW; c += 32) {
       uint32_t v[32];
@@ -261,6 +305,12 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
               o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
             }
             *reinterpret_cast<float4*>(op + 4 * j) = o;
+            if constexpr (EPI == B200VIT_EPI_STORE_F32) {
+              ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+              if (p.out_bf16 != nullptr)
+                *reinterpret_cast<uint2*>(p.out_bf16 + static_cast<size_t>(orow) * p.ldo + col + 4 * j) =
+                    make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            }
           }
         }
       } else {  // BIAS_BF16
@@ -277,6 +327,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
           }
         }
       }
+    }
+    if constexpr (EPI == B200VIT_EPI_STORE_F32) {
+      if (row_ok && p.rowsq_out != nullptr && col0 < p.n)
+        p.rowsq_out[static_cast<size_t>(col0 / CW) * p.m + orow] = ss;
     }
   }
 }
@@ -334,7 +388,8 @@ struct WorkIter {
 template <int BN, int EG, int EPI, bool PAIR>
 __global__ void __launch_bounds__(128 + 128 * EG, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const __grid_constant__ CUtensorMap tma_out, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
+                    const GemmParams p) {
   using C = TileCfg<BN, EG, EPI, PAIR>;
   constexpr int STAGES = C::STAGES;
   constexpr int CW = BN / EG;
@@ -527,22 +582,164 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     WorkIter work(num_tiles, num_kb, unit, num_units, (p.stream_k & 1) != 0);
     Segment sg;
 #ifdef B200_GEMM_TIMING
-    long long e_wait = 0, e_busy = 0, e_prev = clock64(), e_start = e_prev;
+    long long e_wait = 0, e_busy = 0, e_prev = clock64(), e_start = e_prev, e_lastfull = 0;
 #define ESTAMP(v) do { long long _n = clock64(); v += _n - e_prev; e_prev = _n; } while (0)
 #else
 #define ESTAMP(v)
 #endif
+    if constexpr (is_resid_norm(EPI)) {
+      // x += acc + bias with the NEW x in hand: besides the fp32 residual stream the epilogue writes its bf16 copy
+      // (A operand of the next GEMM) and per-row sums of squares (the next RMSNorm's statistics).
+      // A thread can only read ITS row of the accumulator from TMEM, but global memory wants the opposite layout
+      // (a warp instruction should cover whole 128-byte lines), so each 32 x 32 chunk of acc + bias is transposed
+      // through 4 KB of swizzled shared memory: written row-per-thread, read back with 8 lanes per row.  In that
+      // layout the old x arrives by coalesced 128-bit loads -- issued one chunk ahead, the first chunk while the
+      // tile's main loop is still running, so their latency is off the critical path and they do not queue behind
+      // the operand TMA loads -- and the new x and its bf16 copy leave by coalesced stores.
+      // Stream-K: the unit that holds the TAIL k-range of a split tile (always its first segment) reduce-adds its raw
+      // partial into x (TMA) and raises a flag; the unit that holds the HEAD (always its last segment) waits for the
+      // flag before it reads x, so the fp32 addition order is fixed: (x + tail) + (head + bias).
+      static_assert(CW == 128, "row-square partials are per 128-column group");
+      const uint32_t xs = stg;
+      const int row0w = q * 32;
+      const int lr = lane >> 3, lc = (lane & 7) * 4;  // coalesced layout: row 4 i + lr (i = 0..7), columns lc .. lc + 3 of the chunk
+      float* xg = reinterpret_cast<float*>(p.out);
+      auto ld_x = [&](float4 (&dst)[8], int row0, int col) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = row0 + 4 * i + lr;
+          dst[i] = (r < p.m && col + lc + 4 <= p.n) ? ld_global_nc_f4(xg + static_cast<size_t>(r) * p.ldo + col + lc)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      for (; work.next(sg); ++it) {
+        const int row0 = (sg.tile / num_n) * MT + rank * BM + row0w;
+        const int col0 = (sg.tile % num_n) * BN + g * CW;
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        const bool tail = sg.kb0 != 0;
+        float4 xr[8];
+        if (!tail) {
+          if (sg.kb1 != num_kb) {  // head of a split tile: the tail partial of unit + 1 must have landed in x
+            if (lane == 0) {
+              int32_t* flag = p.sync + ((unit + 1) * NCTA + rank) * (4 * EG) + (warp - 4);
+              const long long t0 = clock64();
+              while (ld_acquire_gpu(flag) == 0) {
+                if (clock64() - t0 > 4000000000ll) {
+                  printf("b200vit: stream-K hand-over timed out (block %d warp %d)\n", blockIdx.x, warp);
+                  __trap();
+                }
+              }
+              *flag = 0;  // ready for the next launch
+            }
+            __syncwarp();
+          }
+          ld_x(xr, row0, col0);  // in flight while the tile's main loop finishes
+        }
+        ESTAMP(e_busy);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        ESTAMP(e_wait);
+#ifdef B200_GEMM_TIMING
+        e_lastfull = e_prev;
+#endif
+        const uint32_t taddr = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(row0w) << 16) + g * CW;
+        if (tail) {
+#pragma unroll 1
+          for (int c = 0; c < CW; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c, v);
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_shared_v4(swz128(xs, lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tma_out, xs, col0 + c, row0);
+              bulk_commit();
+            }
+          }
+          if (lane == 0) bulk_wait_read<0>();  // the staging buffer is free for the next tile's generic-proxy writes
+          __syncwarp();
+        } else {
+          float ss[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ss[i] = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < CW; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c, v);
+            const int col = col0 + c;
+            float4 xn[8];
+            if (c + 32 < CW) ld_x(xn, row0, col + 32);  // next chunk's old x
+            const float4 bb = bias4(p.bias, col + lc, p.n);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_shared_v4(swz128(xs, lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + lr;
+              const float4 a = ld_shared_f4(swz128(xs, rr, lane & 7));
+              const float x0 = xr[i].x + (a.x + bb.x), x1 = xr[i].y + (a.y + bb.y);
+              const float x2 = xr[i].z + (a.z + bb.z), x3 = xr[i].w + (a.w + bb.w);
+              ss[i] += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+              const int r = row0 + rr;
+              if (r < p.m && col + lc + 4 <= p.n) {
+                const size_t off = static_cast<size_t>(r) * p.ldo + col + lc;
+                *reinterpret_cast<float4*>(xg + off) = make_float4(x0, x1, x2, x3);
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));
+              }
+            }
+            __syncwarp();  // every lane has read the chunk back before the next one overwrites it
+            if (c + 32 < CW) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xr[i] = xn[i];
+            }
+          }
+          // row sums: the 8 lanes that share a row combine their column partials in a fixed tree
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float s8 = ss[i];
+            s8 += __shfl_xor_sync(0xffffffffu, s8, 1);
+            s8 += __shfl_xor_sync(0xffffffffu, s8, 2);
+            s8 += __shfl_xor_sync(0xffffffffu, s8, 4);
+            const int r = row0 + 4 * i + lr;
+            if ((lane & 7) == 0 && p.rowsq_out != nullptr && r < p.m && col0 < p.n)
+              p.rowsq_out[static_cast<size_t>(col0 / CW) * p.m + r] = s8;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+          else mbar_arrive(&tempty[as]);
+          if (tail) {  // partial landed in x -> hand the tile over to the unit that holds its head
+            bulk_wait<0>();
+            fence_proxy_async_all();
+            st_release_gpu(p.sync + (unit * NCTA + rank) * (4 * EG) + (warp - 4), 1);
+          }
+        }
+      }
+    } else
     for (; work.next(sg); ++it) {
       const int m0 = (sg.tile / num_n) * MT + rank * BM;
       const int n0 = (sg.tile % num_n) * BN;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      float rs = 1.0f;  // the row's RMSNorm scale, fetched while the tile's main loop is still running
+      if constexpr (EPI == B200VIT_EPI_QKV_ROPE || EPI == B200VIT_EPI_SWIGLU) {
+        const int row = m0 + q * 32 + lane;
+        rs = row_rstd(p, row < p.m ? row : 0);
+      }
       ESTAMP(e_busy);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       ESTAMP(e_wait);
       const uint32_t taddr = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16) + g * CW;
-      epilogue_tile<EPI, CW>(taddr, m0 + q * 32, lane, n0 + g * CW, p, &tma_out, stg, sg.kb0 == 0);
+      epilogue_tile<EPI, CW>(taddr, m0 + q * 32, lane, n0 + g * CW, p, &tma_out, stg, sg.kb0 == 0, rs);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -555,7 +752,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #ifdef B200_GEMM_TIMING
     if (blockIdx.x == 10 && warp == 4 && lane == 0) {
       const long long tail = clock64() - e_prev;
-      printf("gemm epilogue warp: total %lld | wait tfull %lld | busy %lld | final bulk wait %lld\n", clock64() - e_start, e_wait, e_busy, tail);
+      printf("gemm epilogue warp: total %lld | wait tfull %lld | busy %lld | final bulk wait %lld | last tile epilogue %lld\n", clock64() - e_start, e_wait, e_busy, tail, e_lastfull ? clock64() - e_lastfull : 0);
     }
 #endif
   }
@@ -608,7 +805,10 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     rc = make_tmap_bf16(&g.tb, a.d_b, a.n, a.k, C::BN_LOAD);
     if (rc) return rc;
     g.to = g.ta;
-    if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, 0);
+    g.taux = g.ta;
+    if (is_resid_norm(EPI)) {
+      rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, 128);  // reduce-add of stream-K tail partials
+    } else if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, 0);
     else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, 128);
     else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, 128);
     else if (EPI == B200VIT_EPI_BIAS_GELU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 64, 128);
@@ -622,11 +822,14 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     }
     int units = num_tiles < max_units ? num_tiles : max_units;
     g.stream_k = 0;
-    if (EPI == B200VIT_EPI_BIAS_RESIDUAL && stream_k_enabled()) {
-      // reduce-add epilogue: partial tiles simply add, so balance the k-blocks over all pairs when the
-      // tile count is not a multiple of the pair count (and each pair still gets >= 8 k-blocks)
-      const long long total = static_cast<long long>(num_tiles) * ((a.k + BK - 1) / BK);
-      if (num_tiles % max_units != 0 && total / max_units >= 8) {
+    if (is_resid_norm(EPI) && a.d_sync != nullptr && stream_k_enabled()) {
+      // balance the k-blocks over all pairs when the tile count is not a multiple of the pair count.  Every unit's
+      // range must be longer than one tile (+ the boundary snapping slack), so a tile is cut at most once and the
+      // cut is always between the LAST segment of unit u (head) and the FIRST segment of unit u + 1 (tail).
+      const int num_kb = (a.k + BK - 1) / BK;
+      const long long total = static_cast<long long>(num_tiles) * num_kb;
+      if (num_tiles % max_units != 0 && total / max_units >= num_kb + 8 &&
+          (max_units + 1) * (PAIR ? 2 : 1) * C::EPI_WARPS <= B200VIT_GEMM_SYNC_INTS) {
         units = max_units;
         g.stream_k = 1;
       }
@@ -635,15 +838,17 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     g.key = a;
     g.valid = true;
   }
-  GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const uint32_t*>(a.d_rope), a.m, a.n, a.k, a.ldo,
-               a.rope_cols, g.stream_k | (weight_prefetch_enabled() ? 0 : 2)};
+  GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const float2*>(a.d_rope),
+               reinterpret_cast<const int2*>(a.d_rope_pos), a.m, a.n, a.k, a.ldo,
+               a.rope_cols, g.stream_k | (weight_prefetch_enabled() ? 0 : 2),
+               reinterpret_cast<__nv_bfloat16*>(a.d_out_bf16), a.d_rowsq_out, a.d_rowsq_in, a.rowsq_parts, a.norm_eps, a.d_sync};
   auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // per instantiation and device
+  if (attr_set.need()) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark();
   }
-  B200_CUDA_OK(launch_kernel(kern, dim3(g.grid), dim3(128 + 128 * EG), C::SMEM_BYTES, stream, PAIR ? 2 : 1, g.ta, g.tb, g.to, p));
+  B200_CUDA_OK(launch_kernel(kern, dim3(g.grid), dim3(128 + 128 * EG), C::SMEM_BYTES, stream, PAIR ? 2 : 1, g.ta, g.tb, g.to, g.taux, p));
   return 0;
 }
 
@@ -661,6 +866,13 @@ int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* c
   if ((reinterpret_cast<uintptr_t>(a.d_a) | reinterpret_cast<uintptr_t>(a.d_b) | reinterpret_cast<uintptr_t>(a.d_out)) & 15)
     return fail(B200VIT_EALIGN, "gemm: A, B and out must be 16-byte aligned");
   const bool needs_bias = a.epilogue != B200VIT_EPI_STORE_F32;
+  if (a.d_rowsq_in != nullptr && (a.rowsq_parts <= 0 || a.rowsq_parts > MAX_ROWSQ_PARTS))
+    return fail(B200VIT_EINVAL, "gemm: d_rowsq_in needs 1 <= rowsq_parts <= 16 (K <= 2048)");
+  if (a.d_rowsq_in != nullptr && a.epilogue != B200VIT_EPI_QKV_ROPE && a.epilogue != B200VIT_EPI_SWIGLU)
+    return fail(B200VIT_EINVAL, "gemm: d_rowsq_in (fused RMSNorm) is implemented by the QKV_ROPE and SWIGLU epilogues");
+  if ((a.d_out_bf16 != nullptr || a.d_rowsq_out != nullptr) && a.epilogue != B200VIT_EPI_STORE_F32 &&
+      a.epilogue != B200VIT_EPI_BIAS_RESIDUAL_NORM)
+    return fail(B200VIT_EINVAL, "gemm: d_out_bf16 / d_rowsq_out are produced by the STORE_F32 and BIAS_RESIDUAL_NORM epilogues");
   if (needs_bias && a.d_bias == nullptr) return fail(B200VIT_EINVAL, "gemm: epilogue needs a bias vector");
   switch (a.epilogue) {
     case B200VIT_EPI_STORE_F32:
@@ -670,12 +882,17 @@ int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* c
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
       return launch_one<256, 2, B200VIT_EPI_BIAS_F32>(a, stream, cache);
     case B200VIT_EPI_QKV_ROPE:
-      if (a.n % 240 || a.rope_cols % 80 || a.ldo % 8 || !a.d_rope)
-        return fail(B200VIT_EINVAL, "gemm: QKV epilogue needs N % 240 == 0, head_dim 80, a rope table");
+      if (a.n % 240 || a.rope_cols % 80 || a.ldo % 8 || !a.d_rope || !a.d_rope_pos ||
+          ((reinterpret_cast<uintptr_t>(a.d_rope) | reinterpret_cast<uintptr_t>(a.d_rope_pos)) & 15))
+        return fail(B200VIT_EINVAL, "gemm: QKV epilogue needs N % 240 == 0, head_dim 80, a 16-byte aligned rope table and row positions");
       return launch_one<240, 3, B200VIT_EPI_QKV_ROPE>(a, stream, cache);
     case B200VIT_EPI_BIAS_RESIDUAL:
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
       return launch_one<256, 2, B200VIT_EPI_BIAS_RESIDUAL>(a, stream, cache);
+    case B200VIT_EPI_BIAS_RESIDUAL_NORM:
+      if (a.n % 8 || a.ldo % 8 || !a.d_out_bf16 || (reinterpret_cast<uintptr_t>(a.d_out_bf16) & 15))
+        return fail(B200VIT_EINVAL, "gemm: BIAS_RESIDUAL_NORM needs N % 8 == 0, ldo % 8 == 0 and a 16-byte aligned d_out_bf16");
+      return launch_one<256, 2, B200VIT_EPI_BIAS_RESIDUAL_NORM>(a, stream, cache);
     case B200VIT_EPI_SWIGLU:
       if (a.n % 16 || a.ldo % 8) return fail(B200VIT_EINVAL, "gemm: SwiGLU needs N % 16 == 0 and ldo % 8 == 0");
       return launch_one<256, 2, B200VIT_EPI_SWIGLU>(a, stream, cache);

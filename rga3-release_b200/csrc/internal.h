@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -21,7 +22,22 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::b200::cuda_fail(_e, #expr); \
   } while (0)
 
-int device_sm_count();
+// "Once per device" guard for per-device state (function attributes, __device__ symbol uploads): a process may
+// drive several GPUs, and cudaFuncSetAttribute / cudaMemcpyToSymbol only affect the current one.  Redoing the set-up
+// from two threads at once is harmless (idempotent), so no lock.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  int dev = 0;
+  bool need() {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return dev < 0 || dev >= 64 || ((done.load(std::memory_order_acquire) >> dev) & 1ull) == 0;
+  }
+  void mark() {
+    if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
+
+int device_sm_count();  // of the current device
 int check_arch();  // 0 if the current device is sm_100, else B200VIT_EARCH
 
 // 2-D bf16 row-major [rows, cols] tensor map, box = [box_rows, 64 cols], SWIZZLE_128B,
@@ -38,7 +54,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols,
 struct GemmPrepared {
   bool valid = false;
   b200vit_gemm_args key;
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, to, taux;
   int grid = 0, stream_k = 0;
 };
 int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* cache = nullptr);

@@ -316,8 +316,8 @@ uint16_t f32_to_bf16_rne(float f) {
 }
 
 int upload_lut() {
-  static bool done = false;
-  if (done) return 0;
+  static DeviceOnce done;  // g_norm_lut is a __device__ symbol: one copy per device
+  if (!done.need()) return 0;
   // HF: mean_t = float32(mean) * 255, std_t = float32(std) * 255; (float(v) - mean_t) / std_t in fp32
   const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
   const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
@@ -332,7 +332,7 @@ int upload_lut() {
     }
   }
   B200_CUDA_OK(cudaMemcpyToSymbol(g_norm_lut, lut, sizeof(lut)));
-  done = true;
+  done.mark();
   return 0;
 }
 
@@ -442,11 +442,11 @@ int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov,
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_bf16) + p.row_base * cols;
       const bool has_ov = ov != nullptr && (ov->h_ops != nullptr || ov->d_ops != nullptr);
       if (patch == SP && tps == STPS && merge == SMG && (reinterpret_cast<uintptr_t>(p.frames) & 3) == 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.need()) {
           B200_CUDA_OK(cudaFuncSetAttribute(overlay_patchify_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
           B200_CUDA_OK(cudaFuncSetAttribute(overlay_patchify_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
-          attr_set = true;
+          attr_set.mark();
         }
         const dim3 sgrid((gw / SMG + SG - 1) / SG, gh / SMG, nf_pad / tps);
         if (has_ov)

@@ -117,6 +117,22 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+// orders generic-proxy accesses (e.g. an acquired flag) against later async-proxy (TMA) accesses of global / shared memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // shared address of 16-byte chunk j of row `row` inside a [rows x 128 B] SWIZZLE_128B tile at `base` (1024-aligned)
 __device__ __forceinline__ uint32_t swz128(uint32_t base, int row, int j) {
   return base + row * 128 + ((j ^ (row & 7)) << 4);
@@ -125,6 +141,13 @@ __device__ __forceinline__ uint32_t swz128(uint32_t base, int row, int j) {
 // same for a [rows x 64 B] SWIZZLE_64B tile (512-aligned): 16-byte chunk index XOR ((row >> 1) & 3)
 __device__ __forceinline__ uint32_t swz64(uint32_t base, int row, int j) {
   return base + row * 64 + ((j ^ ((row >> 1) & 3)) << 4);
+}
+
+// 128-bit global load that does not allocate in L1 (data another SM wrote earlier in the same kernel)
+__device__ __forceinline__ float4 ld_global_nc_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
 }
 
 // ---------------------------------------------------------------- clusters / CTA pairs

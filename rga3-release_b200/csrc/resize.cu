@@ -261,10 +261,10 @@ extern "C" int b200vit_resize_bicubic(const uint8_t* d_in, int32_t t, int32_t h_
   }
   if (need_h) {
     uint8_t* dst = need_v ? ws + lay.tmp : d_out;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.need()) {
       B200_CUDA_OK(cudaFuncSetAttribute(resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RESIZE_H_SMEM_MAX));
-      attr = true;
+      attr.mark();
     }
     // input bytes 256 consecutive outputs can touch: 256 steps of `scale` plus the filter support on both sides
     const double scale = static_cast<double>(w_in) / w_out;

@@ -447,11 +447,11 @@ extern "C" int b200vit_stom_policy(const float* d_tracks, const uint8_t* d_vis, 
     int p2 = 1;
     while (p2 < n_points) p2 <<= 1;
     const int smem = p2 * static_cast<int>(sizeof(float));
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.need()) {
       B200_CUDA_OK(cudaFuncSetAttribute(stom_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         MAX_POINTS * static_cast<int>(sizeof(float))));
-      attr = true;
+      attr.mark();
     }
     stom_flow_kernel<<<t_frames, POLICY_THREADS, smem, stream>>>(d_tracks, d_vis, n_points, key_idx, h, w,
                                                                  reinterpret_cast<float*>(ws + lay.flow_scratch), d_ops);

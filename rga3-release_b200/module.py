@@ -24,6 +24,14 @@ from . import _lib
 from .overlay import OverlaySpec
 
 
+def _norm_device(device) -> torch.device:
+    """torch.device with an explicit CUDA index ("cuda" -> the current device), so device comparisons are exact."""
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    return d
+
+
 class _Holder(nn.Module):
     """Parameter holder with the HF names (weight / bias)."""
 
@@ -36,13 +44,12 @@ class _Holder(nn.Module):
 
 
 class _Plan:
-    """Owns one b200vit_plan (host + device index tables, launch memos).  The activation workspace is NOT per plan:
-    the tower keeps one per slot, sized for the largest grid seen, so a service that sees many resolutions does not
-    accumulate gigabytes of idle workspaces."""
+    """Owns one b200vit_plan (host + device index tables).  Immutable once uploaded, so ONE plan per grid serves every
+    stream / slot.  The activation workspace is NOT per plan: the tower keeps one per slot, sized for the largest grid
+    seen, so a service that sees many resolutions does not accumulate gigabytes of idle workspaces."""
 
-    def __init__(self, grid: Tuple[Tuple[int, int, int], ...], cfg_c, device, slot: int = 0):
+    def __init__(self, grid: Tuple[Tuple[int, int, int], ...], cfg_c, device):
         self.grid = grid
-        self.slot = slot
         arr = (C.c_int64 * (3 * len(grid)))(*[v for g in grid for v in g])
         handle = C.c_void_p()
         _lib.check(_lib.lib().b200vit_plan_create(arr, len(grid), C.byref(cfg_c), C.byref(handle)), "plan_create")
@@ -100,7 +107,7 @@ class B200VisionTower(nn.Module):
         if g("hidden_act", "silu") != "silu":
             raise ValueError("only the SiLU-gated MLP of Qwen2.5-VL is implemented")
         self._dtype = dtype
-        self._device = torch.device(device)
+        self._device = _norm_device(device)
         self.use_cuda_graph = use_cuda_graph
         self.output_fp32 = output_fp32
         if return_dict is None:  # transformers >= 5 returns an object with .pooler_output, 4.49 a tensor
@@ -152,16 +159,26 @@ class B200VisionTower(nn.Module):
 
     def _invalidate(self):
         self._packed = None
+        for q in self._plans.values():      # captured graphs replay the old packed buffer
+            q.graphs.clear()
+
+    def invalidate(self):
+        """Call after editing a parameter in place (``tower.blocks[0].attn.qkv.bias.add_(...)``): the packed device
+        copies are rebuilt by the next forward.  ``load_state_dict`` / ``.to()`` / ``.half()`` do this themselves."""
+        self._invalidate()
 
     def _apply(self, fn, *args, **kwargs):
         """`.to()`, `.cuda()`, `.half()` ...: the HF-named parameters move or change dtype, so the packed copies (and,
-        on a device change, every plan and workspace) are rebuilt lazily by the next forward."""
+        on a device change, every plan and workspace) are rebuilt lazily by the next forward; `dtype` / `device`
+        follow the parameters, as they do on the HF module."""
         out = super()._apply(fn, *args, **kwargs)
         p = next(self.parameters(), None)
-        if p is not None and p.device != self._device:
-            self._device = p.device
+        if p is not None and _norm_device(p.device) != self._device:
+            self._device = _norm_device(p.device)
             self._plans.clear()
             self._workspaces.clear()
+        if p is not None and p.dtype.is_floating_point and p.dtype != self._dtype:
+            self._dtype = p.dtype
         self._invalidate()
         return out
 
@@ -174,48 +191,47 @@ class B200VisionTower(nn.Module):
         m.load_state_dict(sd)
         return m
 
-    # ---- weight packing (once): bf16 [N,K] matrices, gate/up interleave, I -> Ipad zero pad
+    # ---- weight packing (once): b200vit_pack_weights does the bf16 casts, the RMSNorm gamma fold, the gate/up
+    # interleave and the I -> Ipad padding on the device; this method only hands it the HF-named tensors.
     @torch.no_grad()
     def pack_weights(self):
-        d, i = self.hidden_size, self.intermediate_size
-        ipad = (i + 127) // 128 * 128
         dev = self._device
+        params = [p for p in self.parameters()]
+        dt = params[0].dtype
+        code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}.get(dt)
         keep = []
 
-        def bf(t):
-            t = t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
-            keep.append(t)
+        def ptr(t):
+            if code is None or t.dtype != dt or t.device != dev or not t.is_contiguous():
+                t = t.detach().to(device=dev, dtype=dt if code is not None else torch.float32).contiguous()
+                keep.append(t)
             return t.data_ptr()
 
-        def f32(t):
-            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
-            keep.append(t)
-            return t.data_ptr()
-
-        layers = (_lib.LayerWeights * self.depth)()
+        raw_layers = (_lib.RawLayer * self.depth)()
         for li, b in enumerate(self.blocks):
-            lw = layers[li]
-            lw.norm1_w, lw.norm2_w = f32(b.norm1.weight), f32(b.norm2.weight)
-            lw.qkv_w, lw.qkv_b = bf(b.attn.qkv.weight), f32(b.attn.qkv.bias)
-            lw.proj_w, lw.proj_b = bf(b.attn.proj.weight), f32(b.attn.proj.bias)
-            gw = torch.zeros(ipad, 2, d, dtype=torch.float32, device=dev)
-            gw[:i, 0] = b.mlp.gate_proj.weight.float()
-            gw[:i, 1] = b.mlp.up_proj.weight.float()
-            gb = torch.zeros(ipad, 2, dtype=torch.float32, device=dev)
-            gb[:i, 0] = b.mlp.gate_proj.bias.float()
-            gb[:i, 1] = b.mlp.up_proj.bias.float()
-            lw.gateup_w, lw.gateup_b = bf(gw.view(2 * ipad, d)), f32(gb.view(2 * ipad))
-            dw = torch.zeros(d, ipad, dtype=torch.float32, device=dev)
-            dw[:, :i] = b.mlp.down_proj.weight.float()
-            lw.down_w, lw.down_b = bf(dw), f32(b.mlp.down_proj.bias)
-        w = _lib.Weights()
-        w.patch_w = bf(self.patch_embed.proj.weight.reshape(d, -1))
-        w.layers = layers
-        w.merger_ln_w = f32(self.merger.ln_q.weight)
-        w.merger_fc1_w, w.merger_fc1_b = bf(self.merger.mlp["0"].weight), f32(self.merger.mlp["0"].bias)
-        w.merger_fc2_w, w.merger_fc2_b = bf(self.merger.mlp["2"].weight), f32(self.merger.mlp["2"].bias)
-        w.ipad = ipad
-        self._packed = (w, layers, keep)
+            r = raw_layers[li]
+            r.norm1_w, r.norm2_w = ptr(b.norm1.weight), ptr(b.norm2.weight)
+            r.qkv_w, r.qkv_b = ptr(b.attn.qkv.weight), ptr(b.attn.qkv.bias)
+            r.proj_w, r.proj_b = ptr(b.attn.proj.weight), ptr(b.attn.proj.bias)
+            r.gate_w, r.gate_b = ptr(b.mlp.gate_proj.weight), ptr(b.mlp.gate_proj.bias)
+            r.up_w, r.up_b = ptr(b.mlp.up_proj.weight), ptr(b.mlp.up_proj.bias)
+            r.down_w, r.down_b = ptr(b.mlp.down_proj.weight), ptr(b.mlp.down_proj.bias)
+        raw = _lib.RawWeights()
+        raw.dtype = code if code is not None else 0
+        raw.patch_w = ptr(self.patch_embed.proj.weight)
+        raw.layers = raw_layers
+        raw.merger_ln_w = ptr(self.merger.ln_q.weight)
+        raw.merger_fc1_w, raw.merger_fc1_b = ptr(self.merger.mlp["0"].weight), ptr(self.merger.mlp["0"].bias)
+        raw.merger_fc2_w, raw.merger_fc2_b = ptr(self.merger.mlp["2"].weight), ptr(self.merger.mlp["2"].bias)
+        nbytes = int(_lib.lib().b200vit_packed_weights_bytes(C.byref(self._cfg_c)))
+        with torch.cuda.device(dev):
+            buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            base = buf.data_ptr() + ((-buf.data_ptr()) % 256)
+            w, layers = _lib.Weights(), (_lib.LayerWeights * self.depth)()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib().b200vit_pack_weights(C.byref(self._cfg_c), C.byref(raw), base, nbytes, C.byref(w), layers,
+                                                       stream), "pack_weights")
+        self._packed = (w, layers, buf)
         return w
 
     def _weights(self):
@@ -224,53 +240,62 @@ class B200VisionTower(nn.Module):
         return self._packed[0]
 
     # ---- plans
-    def plan_for(self, grid_thw, slot: int = 0) -> _Plan:
-        """Plan (index tables, workspace, launch memos) for this grid.  `slot` selects an independent instance so
-        several clips can be in flight on different CUDA streams (one workspace per slot)."""
+    def plan_for(self, grid_thw) -> _Plan:
+        """Plan (index tables, workspace layout) for this grid; shared by every stream / slot."""
         if isinstance(grid_thw, torch.Tensor):
             grid = tuple(tuple(int(v) for v in row) for row in grid_thw.detach().cpu().tolist())
         else:
             grid = tuple(tuple(int(v) for v in row) for row in np.asarray(grid_thw).reshape(-1, 3).tolist())
-        key = (grid, int(slot))
-        p = self._plans.get(key)
+        p = self._plans.get(grid)
         if p is None:
-            p = _Plan(grid, self._cfg_c, self._device, int(slot))
-            self._plans[key] = p
+            p = _Plan(grid, self._cfg_c, self._device)
+            self._plans[grid] = p
             while len(self._plans) > self.max_plans:       # least recently used first; never the one just made
                 self._plans.popitem(last=False)
         else:
-            self._plans.move_to_end(key)
+            self._plans.move_to_end(grid)
         return p
 
-    def _workspace(self, plan: _Plan) -> int:
-        """1024-byte aligned workspace pointer for this plan's slot, grown (never shrunk) to the largest request."""
-        ws = self._workspaces.get(plan.slot)
+    def _workspace(self, plan: _Plan, slot: int = 0) -> int:
+        """1024-byte aligned workspace pointer of `slot`, grown (never shrunk) to the largest request.  Clips that are
+        in flight at the same time (different CUDA streams) must use different slots."""
+        ws = self._workspaces.get(slot)
         if ws is None or ws[2] < plan.ws_bytes:
             t = torch.empty(plan.ws_bytes + 1024, dtype=torch.uint8, device=self._device)
             ptr = t.data_ptr() + ((-t.data_ptr()) % 1024)
-            self._workspaces[plan.slot] = ws = (t, ptr, plan.ws_bytes)
-            for (_, s), q in self._plans.items():           # captured graphs point into the old buffer
-                if s == plan.slot:
-                    q.graphs.clear()
+            self._workspaces[slot] = ws = (t, ptr, plan.ws_bytes)
+            for q in self._plans.values():                  # captured graphs point into the old buffer
+                q.graphs.clear()
         return ws[1]
 
+    def _check_device(self, t: torch.Tensor, what: str):
+        if not t.is_cuda or _norm_device(t.device) != self._device:
+            raise ValueError(f"B200VisionTower: {what} must be a CUDA tensor on {self._device} (got {t.device}); "
+                             "there is no CPU path and no implicit cross-device copy")
+
     # ---- the hot path
-    def _run(self, plan: _Plan, pixel_values, frames_c, overlay_c, out, last_hidden):
-        stream = torch.cuda.current_stream(self._device).cuda_stream
-        rc = _lib.lib().b200vit_forward(
-            plan.handle, C.byref(self._weights()),
-            pixel_values.data_ptr() if pixel_values is not None else None,
-            C.byref(frames_c) if frames_c is not None else None,
-            C.byref(overlay_c) if overlay_c is not None else None,
-            out.data_ptr(), 1 if out.dtype == torch.float32 else 0,
-            last_hidden.data_ptr() if last_hidden is not None else None,
-            self._workspace(plan), plan.ws_bytes, stream)
+    def _run(self, plan: _Plan, pixel_values, frames_c, overlay_c, out, last_hidden, slot: int = 0):
+        with torch.cuda.device(self._device):      # allocations, lazy uploads and launches go to the tower's device
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            rc = _lib.lib().b200vit_forward(
+                plan.handle, C.byref(self._weights()),
+                pixel_values.data_ptr() if pixel_values is not None else None,
+                C.byref(frames_c) if frames_c is not None else None,
+                C.byref(overlay_c) if overlay_c is not None else None,
+                out.data_ptr(), 1 if out.dtype == torch.float32 else 0,
+                last_hidden.data_ptr() if last_hidden is not None else None,
+                self._workspace(plan, slot), plan.ws_bytes, stream)
         _lib.check(rc, "b200vit_forward")
 
     def _wrap(self, out, last_hidden):
         if self.return_dict:
             return _Output(out, last_hidden)
         return out
+
+    def _check_out(self, out, shape):
+        if tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError(f"out must be a contiguous bf16/fp32 tensor of shape {shape}")
+        self._check_device(out, "out")
 
     @torch.no_grad()
     def forward(self, hidden_states: torch.Tensor, grid_thw, output_last_hidden_state: bool = False,
@@ -279,8 +304,7 @@ class B200VisionTower(nn.Module):
         `out` (optional): contiguous [M/4, out_hidden] bf16/fp32 destination, e.g. the placeholder rows of the LLM's
         `inputs_embeds` (see `splice_span`): the merger epilogue then writes the visual tokens in place and HF's
         boolean-mask `masked_scatter` (modeling_qwen2_5_vl.py:1309-1315) becomes unnecessary."""
-        if not hidden_states.is_cuda:
-            raise ValueError("B200VisionTower.forward: hidden_states must be a CUDA tensor (no CPU path)")
+        self._check_device(hidden_states, "hidden_states")
         plan = self.plan_for(grid_thw)
         kpe = self.in_channels * self.temporal_patch_size * self.patch_size ** 2
         if hidden_states.dim() != 2 or hidden_states.shape[0] != plan.m or hidden_states.shape[1] != kpe:
@@ -290,19 +314,21 @@ class B200VisionTower(nn.Module):
             code = {torch.float32: 0, torch.float16: 1}.get(x.dtype)
             if code is None:
                 raise ValueError(f"unsupported pixel dtype {x.dtype}")
-            xb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-            stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(_lib.lib().b200vit_cast_to_bf16(x.data_ptr(), code, xb.data_ptr(), x.numel(), stream), "cast")
+            with torch.cuda.device(self._device):
+                xb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+                stream = torch.cuda.current_stream(self._device).cuda_stream
+                _lib.check(_lib.lib().b200vit_cast_to_bf16(x.data_ptr(), code, xb.data_ptr(), x.numel(), stream), "cast")
             x = xb
         out_dtype = torch.float32 if self.output_fp32 else self._dtype
+        if out_dtype not in (torch.bfloat16, torch.float32):
+            out_dtype = torch.bfloat16                      # a .half() tower still computes and returns bf16
         if self.use_cuda_graph and not output_last_hidden_state and out is None:
             return self._wrap(self._graph_forward(plan, x, out_dtype), None)
         shape = (plan.m // self.spatial_merge_unit, self.out_hidden_size)
         if out is None:
             out = torch.empty(shape, dtype=out_dtype, device=x.device)
-        elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.bfloat16, torch.float32) \
-                or not out.is_cuda:
-            raise ValueError(f"out must be a contiguous CUDA bf16/fp32 tensor of shape {shape}")
+        else:
+            self._check_out(out, shape)
         last = torch.empty(plan.m, self.hidden_size, dtype=torch.float32, device=x.device) if output_last_hidden_state else None
         self._run(plan, x, None, None, out, last)
         return self._wrap(out, last)
@@ -328,30 +354,36 @@ class B200VisionTower(nn.Module):
         graph, static_in, static_out = g
         static_in.copy_(x)
         graph.replay()
-        return static_out
+        return static_out.clone()   # the graph's own buffer is overwritten by the next replay (two clips of one shape)
 
     @torch.no_grad()
     def forward_frames(self, frames_u8: torch.Tensor, overlay: Optional[OverlaySpec] = None, grid_thw=None,
                        out: Optional[torch.Tensor] = None, slot: int = 0):
         """Fused entry: uint8 frames [T,H,W,3] (CUDA) + optional STOM overlay -> merged embeddings.
-        Equivalent to PIL overlay -> Qwen2VLVideoProcessor(do_resize=False) -> tower."""
+        Equivalent to PIL overlay -> Qwen2VLVideoProcessor(do_resize=False) -> tower.  `slot` selects the workspace:
+        clips in flight on different CUDA streams use different slots."""
         if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
             raise ValueError("frames must be a CUDA uint8 tensor [T,H,W,3]")
+        self._check_device(frames_u8, "frames")
         t, h, w, _ = frames_u8.shape
         if grid_thw is None:
             tps = self.temporal_patch_size
             grid_thw = [[(t + tps - 1) // tps, h // self.patch_size, w // self.patch_size]]
-        plan = self.plan_for(grid_thw, slot)
+        plan = self.plan_for(grid_thw)
         fr = frames_u8.contiguous()
         fc = _lib.Frames(fr.data_ptr(), t, h, w)
+        if overlay is not None:
+            overlay.validate(h, w, self._device)   # Image.alpha_composite raises on a size mismatch; so do we
         oc = overlay.to_c(t) if overlay is not None else None
         out_dtype = torch.float32 if self.output_fp32 else self._dtype
+        if out_dtype not in (torch.bfloat16, torch.float32):
+            out_dtype = torch.bfloat16
         shape = (plan.m // self.spatial_merge_unit, self.out_hidden_size)
         if out is None:
             out = torch.empty(shape, dtype=out_dtype, device=fr.device)
-        elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.bfloat16, torch.float32):
-            raise ValueError(f"out must be a contiguous bf16/fp32 tensor of shape {shape}")
-        self._run(plan, None, fc, oc, out, None)
+        else:
+            self._check_out(out, shape)
+        self._run(plan, None, fc, oc, out, None, slot)
         return self._wrap(out, None)
 
     def profile(self, grid_thw, enable: bool):

@@ -99,6 +99,20 @@ class OverlaySpec:
         return cls(kind=_lib.LAYER_BOX, palette=pal, box=tuple(int(v) for v in box), box_width=max(int(width), 1),
                    ops=list(ops))
 
+    def validate(self, h: int, w: int, device):
+        """The prompt layer must cover the frames exactly: the kernel indexes it with the frame's pitch, and the
+        reference's ``Image.alpha_composite`` (STOM.py:84-87, :157-160) raises on a size mismatch as well."""
+        if self.kind in (_lib.LAYER_RGBA, _lib.LAYER_PALETTE):
+            lay = self.layer
+            want = (h, w, 4) if self.kind == _lib.LAYER_RGBA else (h, w)
+            if lay is None or tuple(lay.shape) != want or lay.dtype != torch.uint8 or not lay.is_contiguous():
+                raise ValueError(f"overlay layer must be a contiguous uint8 tensor of shape {want} matching the frames, "
+                                 f"got {None if lay is None else tuple(lay.shape)} (resize the prompt layer with the frames)")
+            if not lay.is_cuda or lay.device != torch.device(device):
+                raise ValueError(f"overlay layer is on {lay.device}, frames on {device}")
+        if self.device_ops is not None and self.device_ops.device != torch.device(device):
+            raise ValueError(f"overlay device_ops are on {self.device_ops.device}, frames on {device}")
+
     # ---- C view (keeps the backing arrays alive on self)
     def to_c(self, n_frames: int):
         ov = _lib.Overlay()
@@ -228,8 +242,10 @@ def stom_frame_ops_device(pred_tracks: torch.Tensor, pred_visibility: torch.Tens
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=trk.device)
     ops = torch.empty((t, FRAME_OP_BYTES), dtype=torch.uint8, device=trk.device)
     s = stream if stream is not None else torch.cuda.current_stream(trk.device).cuda_stream
-    _lib.check(l.b200vit_stom_policy(trk.data_ptr(), vis.data_ptr(), t, n, int(key_idx), int(mask_shape), int(h), int(w),
-                                     lay_ptr, ops.data_ptr(), ws.data_ptr(), ws_bytes, s), "stom_policy")
+    with torch.cuda.device(trk.device):
+        rc = l.b200vit_stom_policy(trk.data_ptr(), vis.data_ptr(), t, n, int(key_idx), int(mask_shape), int(h), int(w),
+                                   lay_ptr, ops.data_ptr(), ws.data_ptr(), ws_bytes, s)
+    _lib.check(rc, "stom_policy")
     ops._keep = (trk, vis, ws, layer_rgba)  # inputs stay alive until the enqueued kernels have consumed them
     return ops, (min(h, w) // 20 if mask_shape else -1)
 

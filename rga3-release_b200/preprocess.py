@@ -57,8 +57,9 @@ def resize_frames(frames_u8: torch.Tensor, out_h: int, out_w: int, out: Optional
     ws_bytes = int(l.b200vit_resize_workspace_bytes(t, h, w, out_h, out_w))
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=fr.device)
     s = stream if stream is not None else torch.cuda.current_stream(fr.device).cuda_stream
-    _lib.check(l.b200vit_resize_bicubic(fr.data_ptr(), t, h, w, out.data_ptr(), out_h, out_w, ws.data_ptr(), ws_bytes, s),
-               "resize")
+    with torch.cuda.device(fr.device):
+        rc = l.b200vit_resize_bicubic(fr.data_ptr(), t, h, w, out.data_ptr(), out_h, out_w, ws.data_ptr(), ws_bytes, s)
+    _lib.check(rc, "resize")
     out._keep = (fr, ws)  # inputs stay alive until the enqueued kernels have run
     return out
 

@@ -19,24 +19,49 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def pack_rope(cos, sin):
-    """[M,40] fp32 cos / sin -> [M,40] fp16 (cos, sin) pairs viewed as int32 (what the QKV epilogue reads)."""
-    return torch.stack([cos.to(torch.float16), sin.to(torch.float16)], dim=-1).contiguous().view(torch.int32).reshape(cos.shape)
+def make_rope(m, seed, side=50):
+    """Random rotary inputs in the form the QKV epilogue reads them (HF :382-409 before / after the pos_ids gather):
+    a [side, 20, 2] fp32 (cos, sin) table by coordinate and [m, 2] int32 (hpos, wpos) per row.  Also returns the
+    gathered [m, 40] cos / sin an HF-style reference needs."""
+    g = torch.Generator().manual_seed(seed)
+    ang = torch.randn(side, 20, generator=g) * 3.0
+    pos = torch.randint(0, side, (m, 2), generator=g, dtype=torch.int32)
+    table = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+    full = torch.cat([ang[pos[:, 0].long()], ang[pos[:, 1].long()]], dim=-1)      # [m, 40]
+    return (table.to(DEV), pos.to(DEV)), full.cos(), full.sin()
 
 
-def run_gemm(a, b, epi, out, bias=None, row_map=None, rope=None, ldo=None, rope_cols=0):
+def run_gemm(a, b, epi, out, bias=None, row_map=None, rope=None, ldo=None, rope_cols=0, out_bf16=None, rowsq_out=None,
+             rowsq_in=None, eps=1e-6, sync=None):
     g = _lib.GemmArgs()
     g.d_a, g.d_b, g.d_out = a.data_ptr(), b.data_ptr(), out.data_ptr()
     g.d_bias = bias.data_ptr() if bias is not None else None
     g.d_row_map = row_map.data_ptr() if row_map is not None else None
-    g.d_rope = rope.data_ptr() if rope is not None else None
+    if rope is not None:
+        g.d_rope, g.d_rope_pos = rope[0].data_ptr(), rope[1].data_ptr()
     g.m, g.k = a.shape
     g.n = b.shape[0]
     g.ldo = ldo if ldo is not None else out.shape[1]
     g.rope_cols = rope_cols
     g.epilogue = epi
+    g.d_out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    g.d_rowsq_out = rowsq_out.data_ptr() if rowsq_out is not None else None
+    if rowsq_in is not None:
+        g.d_rowsq_in, g.rowsq_parts, g.norm_eps = rowsq_in.data_ptr(), rowsq_in.shape[0], eps
+    g.d_sync = sync.data_ptr() if sync is not None else None
     _lib.check(_lib.lib().b200vit_gemm(C.byref(g), _stream()), "gemm")
     torch.cuda.synchronize()
+
+
+def rowsq_parts(x):
+    """[ceil(N/128), M] per-row sums of squares over each 128-column group (fp64 reference)."""
+    m, n = x.shape
+    parts = (n + 127) // 128
+    out = torch.zeros(parts, m, dtype=torch.float64)
+    xd = x.double().cpu()
+    for i in range(parts):
+        out[i] = (xd[:, i * 128:(i + 1) * 128] ** 2).sum(-1)
+    return out
 
 
 def rnd(shape, seed, scale=1.0, dtype=torch.bfloat16):
@@ -77,10 +102,9 @@ def test_gemm_qkv_rope(m, d):
     nh = d // 80
     a, b = rnd((m, d), 4), rnd((3 * d, d), 5, 0.05)
     bias = rnd((3 * d,), 6, 0.1, torch.float32)
-    ang = rnd((m, 40), 7, 3.0, torch.float32)
-    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    rope, cos, sin = make_rope(m, 7)
     out = torch.zeros(m, 3 * d, dtype=torch.bfloat16, device=DEV)
-    run_gemm(a, b, _lib.EPI_QKV_ROPE, out, bias=bias, rope=pack_rope(cos, sin), rope_cols=2 * d)
+    run_gemm(a, b, _lib.EPI_QKV_ROPE, out, bias=bias, rope=rope, rope_cols=2 * d)
     qkv = (a.float() @ b.float().t() + bias).cpu().reshape(m, 3, nh, 80)
     c80 = torch.cat([cos, cos], -1).cpu()
     s80 = torch.cat([sin, sin], -1).cpu()
@@ -97,6 +121,119 @@ def test_gemm_bias_residual(m, n, k):
     x = x0.clone()
     run_gemm(a, b, _lib.EPI_BIAS_RESIDUAL, x, bias=bias)
     close(x, x0 + a.float() @ b.float().t() + bias, 1e-3)
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 160, 1176), (4096, 1280, 1176)])
+def test_gemm_store_f32_emits_norm_inputs(m, n, k):
+    """Patch-embed epilogue of the fused-RMSNorm path: besides the fp32 rows (window order) it writes their bf16 copy
+    and the per-128-column partial row sums of squares."""
+    a, b = rnd((m, k), 1), rnd((n, k), 2, 0.05)
+    perm = torch.randperm(m, generator=torch.Generator().manual_seed(3)).to(torch.int32).to(DEV)
+    out = torch.zeros(m, n, dtype=torch.float32, device=DEV)
+    ob = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+    parts = (n + 127) // 128
+    rs = torch.zeros(parts, m, dtype=torch.float32, device=DEV)
+    run_gemm(a, b, _lib.EPI_STORE_F32, out, row_map=perm, out_bf16=ob, rowsq_out=rs)
+    ref = torch.empty_like(out)
+    ref[perm.long()] = a.float() @ b.float().t()
+    close(out, ref, 1e-3)
+    assert torch.equal(ob, out.to(torch.bfloat16))                      # the copy is the rounding of what was stored
+    want = rowsq_parts(out)
+    assert torch.allclose(rs.double().cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("m,n,k,stream_k", [(300, 160, 256, False), (2048, 1280, 3456, False), (8192, 1280, 1280, True),
+                                            (8192, 1280, 3456, True), (5000, 1280, 1280, True)])
+def test_gemm_bias_residual_norm(m, n, k, stream_k):
+    """x += A W^T + b with the new x in hand: fp32 x, its bf16 copy and the row-square partials; with the stream-K
+    hand-over scratch the result is bit-identical run to run and to the whole-tile schedule up to fp32 add order."""
+    a, b = rnd((m, k), 8), rnd((n, k), 9, 0.05)
+    bias = rnd((n,), 10, 0.1, torch.float32)
+    x0 = rnd((m, n), 11, 1.0, torch.float32)
+    sync = torch.zeros(_lib.GEMM_SYNC_INTS, dtype=torch.int32, device=DEV) if stream_k else None
+    parts = (n + 127) // 128
+    runs = []
+    for _ in range(3 if stream_k else 1):
+        x = x0.clone()
+        xb = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+        rs = torch.full((parts, m), -1.0, dtype=torch.float32, device=DEV)
+        run_gemm(a, b, _lib.EPI_BIAS_RESIDUAL_NORM, x, bias=bias, out_bf16=xb, rowsq_out=rs, sync=sync)
+        runs.append((x, xb, rs))
+        if sync is not None:
+            assert int(sync.abs().sum()) == 0                            # every launch leaves the flags zeroed
+    x, xb, rs = runs[0]
+    close(x, x0 + a.float() @ b.float().t() + bias, 1e-3)
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    assert torch.allclose(rs.double().cpu(), rowsq_parts(x), rtol=1e-5, atol=1e-6)
+    for x2, xb2, rs2 in runs[1:]:
+        assert torch.equal(x2, x) and torch.equal(xb2, xb) and torch.equal(rs2, rs)
+
+
+def test_gemm_fused_rmsnorm_consumers():
+    """QKV and SwiGLU epilogues with d_rowsq_in: equal to RMSNorm(x, gamma) @ W^T computed the HF way, when gamma is
+    folded into W's columns and the A operand is the bf16 copy of the raw x (HF modeling :57-71)."""
+    m, d, ipad = 1000, 1280, 256
+    x = rnd((m, d), 20, 3.0, torch.float32) * (1 + torch.arange(m, device=DEV).float().unsqueeze(1) / 100)  # rows of very different scale
+    gamma = 1 + 0.1 * rnd((d,), 21, 1.0, torch.float32)
+    xb = x.to(torch.bfloat16)
+    rs_in = rowsq_parts(x).float().to(DEV)
+    normed = (x.double() * torch.rsqrt((x.double() ** 2).mean(-1, keepdim=True) + 1e-6)) * gamma.double()
+    # qkv
+    w = rnd((3 * d, d), 22, 0.05, torch.float32)
+    bias = rnd((3 * d,), 23, 0.1, torch.float32)
+    rope, cos, sin = make_rope(m, 24)
+    out = torch.zeros(m, 3 * d, dtype=torch.bfloat16, device=DEV)
+    run_gemm(xb, (w * gamma).to(torch.bfloat16), _lib.EPI_QKV_ROPE, out, bias=bias, rope=rope, rope_cols=2 * d, rowsq_in=rs_in)
+    qkv = (normed @ w.double().t() + bias.double()).float().cpu().reshape(m, 3, d // 80, 80)
+    c80, s80 = torch.cat([cos, cos], -1).cpu(), torch.cat([sin, sin], -1).cpu()
+    q, k = tower_ref.rope_ref(qkv[:, 0], qkv[:, 1], c80, s80)
+    close(out, torch.stack([q, k, qkv[:, 2]], 1).reshape(m, 3 * d), 1e-2)
+    # gate/up
+    w2 = rnd((2 * ipad, d), 25, 0.05, torch.float32)
+    b2 = rnd((2 * ipad,), 26, 0.1, torch.float32)
+    out2 = torch.zeros(m, ipad, dtype=torch.bfloat16, device=DEV)
+    run_gemm(xb, (w2 * gamma).to(torch.bfloat16), _lib.EPI_SWIGLU, out2, bias=b2, ldo=ipad, rowsq_in=rs_in)
+    z = (normed @ w2.double().t() + b2.double()).float()
+    close(out2, torch.nn.functional.silu(z[:, 0::2]) * z[:, 1::2], 1e-2)
+
+
+def test_pack_weights_c_abi_matches_torch_restatement():
+    """b200vit_pack_weights (host or device pointers, fp32/bf16 sources) == the packing rule restated in torch."""
+    from oracle import hf_ref
+    cfgk = dict(hf_ref.CFG_SMALL)
+    cfg = tower_ref.TowerCfg(**cfgk)
+    sd = hf_ref.make_state_dict(cfg, seed=4)
+    d, i = cfg.hidden_size, cfg.intermediate_size
+    ipad = (i + 127) // 128 * 128
+    for dt, on_dev in ((torch.float32, False), (torch.bfloat16, True)):
+        t = vit.B200VisionTower(cfgk, device=DEV if on_dev else "cpu", dtype=dt, return_dict=False)
+        t.load_state_dict(sd)
+        t._device = torch.device(DEV, torch.cuda.current_device())      # host-resident parameters, packed buffer on the GPU
+        w = t.pack_weights()
+        torch.cuda.synchronize()
+        lw = w.layers[1]
+        src = {k: v.to(dt).float() for k, v in sd.items()}
+
+        def dev_tensor(ptr, shape, dtype):
+            n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            view = type("DevView", (), {"__cuda_array_interface__": dict(shape=(n,), typestr="|u1", data=(int(ptr), False), version=2)})()
+            return torch.as_tensor(view, device=DEV).clone().view(dtype).reshape(shape)
+
+        g1, g2 = src["blocks.1.norm1.weight"], src["blocks.1.norm2.weight"]
+        qkv = dev_tensor(lw.qkv_w, (3 * d, d), torch.bfloat16).cpu()
+        assert torch.equal(qkv, (src["blocks.1.attn.qkv.weight"] * g1).to(torch.bfloat16))
+        gu = dev_tensor(lw.gateup_w, (ipad, 2, d), torch.bfloat16).cpu()
+        assert torch.equal(gu[:i, 0], (src["blocks.1.mlp.gate_proj.weight"] * g2).to(torch.bfloat16))
+        assert torch.equal(gu[:i, 1], (src["blocks.1.mlp.up_proj.weight"] * g2).to(torch.bfloat16))
+        assert int(gu[i:].abs().sum()) == 0
+        gb = dev_tensor(lw.gateup_b, (ipad, 2), torch.float32).cpu()
+        assert torch.equal(gb[:i, 1], src["blocks.1.mlp.up_proj.bias"]) and float(gb[i:].abs().sum()) == 0
+        dw = dev_tensor(lw.down_w, (d, ipad), torch.bfloat16).cpu()
+        assert torch.equal(dw[:, :i], src["blocks.1.mlp.down_proj.weight"].to(torch.bfloat16)) and int(dw[:, i:].abs().sum()) == 0
+        pw = dev_tensor(w.patch_w, (d, 1176), torch.bfloat16).cpu()
+        assert torch.equal(pw, src["patch_embed.proj.weight"].reshape(d, -1).to(torch.bfloat16))
+        fc2b = dev_tensor(w.merger_fc2_b, (cfg.out_hidden_size,), torch.float32).cpu()
+        assert torch.equal(fc2b, src["merger.mlp.2.bias"])
 
 
 @pytest.mark.parametrize("m,ipad,k", [(300, 256, 160), (1024, 3456, 1280)])
@@ -348,3 +485,14 @@ def test_clock_probe_reports_a_plausible_sm_clock():
     assert 50000 <= ns < 5_000_000
     assert 500.0 < cycles / ns * 1e3 < 2500.0          # MHz
     assert _lib.lib().b200vit_clock_probe(None, 1000, _stream()) == -1
+
+
+def test_c_abi_demo_runs_on_the_gpu(tmp_path):
+    """The plain-C host program (examples/c_abi_demo.c) drives the device through the C ABI alone: an exact GEMM, then
+    b200vit_pack_weights from host arrays + b200vit_forward from frames, reproducible bit for bit."""
+    import subprocess
+    from test_host_cpu import build_c_demo
+    exe = build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches against the host loop" in r.stdout and "device calls ok" in r.stdout, r.stdout

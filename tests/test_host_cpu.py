@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in b200vit.h but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.b200vit_version() == 2
+    assert lib.b200vit_version() == _lib.VERSION == 3
 
 
 @pytest.mark.parametrize("grid", [[[2, 8, 12]], [[8, 32, 32]], [[1, 6, 10], [2, 18, 14]], [[1, 2, 2]], [[3, 48, 48]]])
@@ -51,9 +51,14 @@ def test_plan_host_arrays_match_oracle(grid):
     cos = p.get(_lib.PLAN_ROPE_COS, np.float32).reshape(m, 40)
     sin = p.get(_lib.PLAN_ROPE_SIN, np.float32).reshape(m, 40)
     assert np.abs(cos - np.cos(ang)).max() < 2e-6 and np.abs(sin - np.sin(ang)).max() < 2e-6
-    packed = p.get(_lib.PLAN_ROPE_PACKED, np.uint32).reshape(m, 40)
-    assert np.array_equal(packed & 0xFFFF, cos.astype(np.float16).view(np.uint16).astype(np.uint32))
-    assert np.array_equal(packed >> 16, sin.astype(np.float16).view(np.uint16).astype(np.uint32))
+    # what the QKV epilogue reads: HF's table by coordinate (fp32, as HF rotates, :149-167) + window-ordered positions;
+    # gathering one with the other reproduces the [M, 40] tables above bit for bit
+    tab = p.get(_lib.PLAN_ROPE_TABLE, np.float32).reshape(-1, 20, 2)
+    pos = p.get(_lib.PLAN_ROPE_POS, np.int32).reshape(m, 2)
+    assert tab.shape[0] == max(max(g[1], g[2]) for g in grid)
+    assert np.array_equal(pos, index_ref.reorder_rows_ref(index_ref.rope_pos_ids_ref(grid), wi))
+    gathered = np.concatenate([tab[pos[:, 0]], tab[pos[:, 1]]], axis=1)
+    assert np.array_equal(gathered[..., 0], cos) and np.array_equal(gathered[..., 1], sin)
 
 
 def test_plan_rejects_bad_grids():
@@ -152,19 +157,32 @@ def test_gather_tokens_gloo_world2(tmp_path):
     assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_header_is_plain_c_and_links(tmp_path):
-    """include/b200vit.h compiles as C99 (-pedantic: no C++ types cross the ABI) and a plain-C host program links
-    against libb200vit.so and builds a plan on the host (examples/c_abi_demo.c)."""
+def build_c_demo(tmp_path):
+    """gcc -std=c99 -pedantic -Werror on examples/c_abi_demo.c against libb200vit.so (+ libcudart for memory calls)."""
     import shutil
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     vit.lib()  # make sure the library exists (raises with the build hint otherwise)
     libdir = os.path.join(ROOT, "rga3-release_b200")
+    cuda_lib = next((d for d in ("/usr/local/cuda/lib64", "/usr/local/cuda/targets/x86_64-linux/lib")
+                     if os.path.exists(os.path.join(d, "libcudart.so"))), None)
+    if cuda_lib is None:
+        pytest.skip("libcudart.so not found")
     exe = str(tmp_path / "c_abi_demo")
     cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lb200vit", f"-Wl,-rpath,{libdir}", "-o", exe]
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lb200vit", "-L", cuda_lib, "-lcudart", "-lm",
+           f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda_lib}", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    return exe
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/b200vit.h compiles as C99 (-pedantic: no C++ types cross the ABI) and a plain-C host program links
+    against libb200vit.so and builds a plan on the host (examples/c_abi_demo.c; its device half runs in the GPU test
+    tests/test_gpu_ops.py::test_c_abi_demo_runs_on_the_gpu)."""
+    exe = build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert r.returncode == 0, r.stderr
-    assert "b200vit version 2" in r.stdout and "workspace bytes: 222691328" in r.stdout
+    assert "b200vit version 3" in r.stdout and "launches per forward: 165" in r.stdout and "window_index holds 16384 bytes" in r.stdout
+    assert "no GPU: device calls skipped" in r.stdout

@@ -44,12 +44,23 @@ def gemm_fn(m, n, k, epi, ldo=None, rope=False, out_dtype=torch.bfloat16):
     bias = torch.randn(n, device=DEV)
     ocols = ldo if ldo else n
     out = torch.zeros(m, ocols, dtype=out_dtype, device=DEV)
-    rope_t = torch.randint(0, 2 ** 30, (m, 40), dtype=torch.int32, device=DEV) & 0x3BFF3BFF  # finite fp16 pairs
+    rope_t = torch.rand(64, 20, 2, device=DEV) * 2 - 1  # fp32 (cos, sin) by coordinate
+    rope_pos = torch.randint(0, 32, (m, 2), dtype=torch.int32, device=DEV)
+    fused = os.environ.get("FUSED", "1") != "0"
+    xb = torch.zeros(m, ocols, dtype=torch.bfloat16, device=DEV)
+    parts = (n + 127) // 128
+    rowsq = torch.rand(16, m, device=DEV) * 100 + 1
+    sync = torch.zeros(_lib.GEMM_SYNC_INTS, dtype=torch.int32, device=DEV)
     g = _lib.GemmArgs()
     g.d_a, g.d_b, g.d_out, g.d_bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr()
-    g.d_rope = rope_t.data_ptr()
+    g.d_rope, g.d_rope_pos = rope_t.data_ptr(), rope_pos.data_ptr()
     g.m, g.n, g.k, g.ldo, g.rope_cols, g.epilogue = m, n, k, ocols, (2 * n // 3 if rope else 0), epi
-    keep = (a, b, bias, out, rope_t)
+    if epi == _lib.EPI_BIAS_RESIDUAL_NORM or (epi == _lib.EPI_STORE_F32 and fused):
+        g.d_out_bf16, g.d_rowsq_out = xb.data_ptr(), rowsq.data_ptr()
+        g.d_sync = sync.data_ptr() if os.environ.get("STREAM_K", "1") != "0" else None
+    if epi in (_lib.EPI_QKV_ROPE, _lib.EPI_SWIGLU) and fused:
+        g.d_rowsq_in, g.rowsq_parts, g.norm_eps = rowsq.data_ptr(), 10, 1e-6
+    keep = (a, b, bias, out, rope_t, rope_pos, xb, rowsq, sync)
 
     def fn():
         _lib.check(_lib.lib().b200vit_gemm(C.byref(g), stream()), "gemm")
@@ -63,9 +74,11 @@ def main():
     shapes = [
         ("patch_embed", M, D, 1176, _lib.EPI_STORE_F32, None, False, torch.float32),
         ("qkv_rope", M, 3 * D, D, _lib.EPI_QKV_ROPE, None, True, torch.bfloat16),
-        ("proj_resid", M, D, D, _lib.EPI_BIAS_RESIDUAL, None, False, torch.float32),
+        ("proj_resid", M, D, D, _lib.EPI_BIAS_RESIDUAL_NORM, None, False, torch.float32),
+        ("proj_old", M, D, D, _lib.EPI_BIAS_RESIDUAL, None, False, torch.float32),
         ("gateup_swiglu", M, 2 * IPAD, D, _lib.EPI_SWIGLU, IPAD, False, torch.bfloat16),
-        ("down_resid", M, D, IPAD, _lib.EPI_BIAS_RESIDUAL, None, False, torch.float32),
+        ("down_resid", M, D, IPAD, _lib.EPI_BIAS_RESIDUAL_NORM, None, False, torch.float32),
+        ("down_old", M, D, IPAD, _lib.EPI_BIAS_RESIDUAL, None, False, torch.float32),
         ("merger_fc1", M // 4, 4 * D, 4 * D, _lib.EPI_BIAS_GELU, None, False, torch.bfloat16),
         ("merger_fc2", M // 4, 3584, 4 * D, _lib.EPI_BIAS_BF16, None, False, torch.bfloat16),
     ]
