@@ -204,7 +204,7 @@ def test_cfg4_long_video_slice_independence():
     # not bit-equal: M differs, so the stream-K split points (which tiles add their k-range in two pieces) differ and
     # flip individual bf16 roundings downstream; the agreement stays at bf16-rounding level
     cos, rel = parity(torch.cat([a, b]), whole)
-    assert cos >= 0.9999 and rel <= 1e-2, (cos, rel)
+    assert cos >= 0.9999 and rel <= REL_MAX, (cos, rel)
 
 
 def test_cfg3_batched_clips_equal_per_clip_runs():
@@ -217,8 +217,10 @@ def test_cfg3_batched_clips_equal_per_clip_runs():
     whole = t(pv, torch.tensor([[16, 32, 32]] * n))
     assert whole.shape == (n * 4096, 3584)
     parts = [t(pv[i * 16384:(i + 1) * 16384], torch.tensor([[16, 32, 32]])) for i in range(n)]
+    # same reasoning as above: the two schedules cut different tiles in two, so single bf16 roundings flip; both results
+    # are bf16 renderings of the same fp32 function, so they agree within the path's own tolerance
     cos, rel = parity(torch.cat(parts), whole)
-    assert cos >= 0.9999 and rel <= 1e-2, (cos, rel)
+    assert cos >= 0.9999 and rel <= REL_MAX, (cos, rel)
 
 
 def test_ragged_grid_7b_vs_hf_fp32():
