@@ -239,6 +239,23 @@ int b200vit_stom_policy(const float* d_tracks, const uint8_t* d_vis, int32_t t_f
                         int32_t mask_shape, int32_t h, int32_t w, const uint8_t* d_layer_rgba, b200vit_frame_op* d_ops,
                         void* d_workspace, size_t workspace_bytes, b200vit_stream stream);
 
+/* Prompt-layer rasterisers: the mask and scribble prompts of /root/reference/utils/visual_prompt_generator.py
+ * (draw_mask :268-274 = ImageDraw.polygon(coords, fill) per contour; draw_scribble :230-252 = one
+ * ImageDraw.line([prev, cur], width) per step of a cubic Bezier sampled at 1000 * max(W,H)/anchor points), drawn on
+ * the GPU into a uint8 [h, w] palette layer (the d_layer of a B200VIT_LAYER_PALETTE overlay): every pixel Pillow
+ * would paint gets `index`, the others are left as they are (zero the layer first).  Coverage is Pillow's bit for
+ * bit (integer-truncated vertices, float32 scanline crossings, ROUND_UP / ROUND_DOWN span ends, the corner rules of
+ * polygon_generic, ImagingDrawWideLine's quadrilateral; Bresenham for width <= 1).  Vertex lists are HOST arrays of
+ * doubles, as ImageDraw hands them to the C library.                                                              */
+int b200vit_raster_polygons(const double* h_xy, const int32_t* h_counts, int32_t n_polygons, int32_t h, int32_t w,
+                            uint8_t index, uint8_t* d_layer, b200vit_stream stream);
+/* n_points - 1 separate two-point lines (x0,y0)-(x1,y1), (x1,y1)-(x2,y2), ... of one width (no joints)           */
+int b200vit_raster_lines(const double* h_xy, int32_t n_points, int32_t width, int32_t h, int32_t w, uint8_t index,
+                         uint8_t* d_layer, b200vit_stream stream);
+/* Host helper: the n_points Bezier samples of draw_scribble (:244-246) for control points h_ctrl8 =
+ * {p0x,p0y,p1x,p1y,p2x,p2y,p3x,p3y}, evaluated exactly as the Python expression is (float64, t from np.linspace). */
+int b200vit_scribble_points(const double* h_ctrl8, int32_t n_points, double* h_xy_out);
+
 /* Overlay + normalise + patchify: bf16 [M, 3*tp*14*14] in processor order.    */
 int b200vit_overlay_patchify(const b200vit_frames* frames, const b200vit_overlay* overlay, int patch, int tps,
                              int merge, void* d_out_bf16, b200vit_stream stream);

@@ -10,6 +10,9 @@ from .preprocess import fit_frames, resize_frames, smart_resize
 from .pipeline import ClipPipeline
 from .overlay import (FrameOp, OverlaySpec, frame_ops_from_bytes, shift_from_flow, stom_frame_ops,
                       stom_frame_ops_device)
+from .prompts import (get_bbox_from_mask, lines_layer, mask_layer, prompt_alpha, prompt_line_width, scribble_layer,
+                      scribble_points)
 
 __all__ = ["B200VisionTower", "install", "splice_span", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "stom_frame_ops_device", "frame_ops_from_bytes", "lib", "shard_clips", "shard_slices", "gather_tokens", "smart_resize", "resize_frames", "fit_frames", "ClipPipeline",
-           "B200VitError"]
+           "B200VitError", "mask_layer", "scribble_layer", "lines_layer", "scribble_points", "prompt_alpha", "prompt_line_width",
+           "get_bbox_from_mask"]

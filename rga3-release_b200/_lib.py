@@ -99,6 +99,11 @@ EXPORTS = {
     "b200vit_stom_policy_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "b200vit_stom_policy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200vit_raster_polygons": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_uint8, C.c_void_p, C.c_void_p]),
+    "b200vit_raster_lines": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint8,
+                                       C.c_void_p, C.c_void_p]),
+    "b200vit_scribble_points": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double)]),
     "b200vit_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200vit_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "b200vit_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p]),

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 # directory) -- e.g. with B200VIT_NVCC_EXTRA=-DB200_GEMM_TIMING; _lib.py loads it when B200VIT_LIB names it.
 TAG = os.environ.get("B200VIT_BUILD_TAG", "")
 LIB = os.path.join(HERE, f"libb200vit_{TAG}.so" if TAG else "libb200vit.so")
-SOURCES = ["common.cu", "gemm.cu", "attention_tc.cu", "elementwise.cu", "overlay.cu", "stom_policy.cu", "resize.cu", "pack.cu", "api.cu"]
+SOURCES = ["common.cu", "gemm.cu", "attention_tc.cu", "elementwise.cu", "overlay.cu", "stom_policy.cu", "resize.cu", "pack.cu", "raster.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"] + os.environ.get("B200VIT_NVCC_EXTRA", "").split()
 
