@@ -10,9 +10,13 @@ from .preprocess import fit_frames, resize_frames, smart_resize
 from .pipeline import ClipPipeline
 from .overlay import (FrameOp, OverlaySpec, frame_ops_from_bytes, shift_from_flow, stom_frame_ops,
                       stom_frame_ops_device)
+from .mrope import mrope_position_ids
+from .sampling import (clip_indices_with_key_frame, get_dense_indices, get_sparse_indices, stage_clip, uniform_sample,
+                       video_frame_indices)
 from .prompts import (get_bbox_from_mask, lines_layer, mask_layer, prompt_alpha, prompt_line_width, scribble_layer,
                       scribble_points)
 
 __all__ = ["B200VisionTower", "install", "splice_span", "OverlaySpec", "FrameOp", "shift_from_flow", "stom_frame_ops", "stom_frame_ops_device", "frame_ops_from_bytes", "lib", "shard_clips", "shard_slices", "gather_tokens", "smart_resize", "resize_frames", "fit_frames", "ClipPipeline",
            "B200VitError", "mask_layer", "scribble_layer", "lines_layer", "scribble_points", "prompt_alpha", "prompt_line_width",
-           "get_bbox_from_mask"]
+           "get_bbox_from_mask", "mrope_position_ids", "uniform_sample", "get_sparse_indices", "get_dense_indices", "video_frame_indices",
+           "clip_indices_with_key_frame", "stage_clip"]
