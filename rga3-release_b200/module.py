@@ -422,6 +422,8 @@ def install(model, **kw):
     ``model.visual`` (4.49, used by /root/reference/train_joint.py:190)."""
     holder = model.model if hasattr(getattr(model, "model", None), "visual") else model
     hf_tower = holder.visual
-    tower = B200VisionTower.from_hf(hf_tower, device=next(hf_tower.parameters()).device, **kw)
+    p0 = next(hf_tower.parameters())
+    kw.setdefault("dtype", p0.dtype)                        # `tower.dtype` is what HF casts pixel_values to (:1148)
+    tower = B200VisionTower.from_hf(hf_tower, device=p0.device, **kw)
     holder.visual = tower
     return tower

@@ -186,3 +186,36 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert r.returncode == 0, r.stderr
     assert "b200vit version 3" in r.stdout and "launches per forward: 165" in r.stdout and "window_index holds 16384 bytes" in r.stdout
     assert "no GPU: device calls skipped" in r.stdout
+
+
+def test_install_into_the_reference_unigr_wrapper():
+    """SURVEY.md 8c recipe, in the build container only (needs /root/reference): the reference's own UniGRModel
+    (model/qwen_2_5_vl_sam2.py:104) accepts ``install()``: the tower lands where get_video_features looks for it, keeps
+    HF's state_dict keys and the attributes HF reads (dtype, spatial_merge_size).  The forward itself runs on the GPU
+    against the fixture this class produced (tests/test_gpu_unigr.py)."""
+    import types
+    if not os.path.exists("/root/reference/model/qwen_2_5_vl_sam2.py"):
+        pytest.skip("/root/reference is not available here")
+    from unigr_case import unigr_config_kwargs
+    saved = sys.modules.get("qwen_vl_utils")
+    sys.modules["qwen_vl_utils"] = types.SimpleNamespace(process_vision_info=None)
+    sys.path.insert(0, "/root/reference")
+    try:
+        from model.qwen_2_5_vl_sam2 import UniGRConfig, UniGRModel
+        torch.manual_seed(0)
+        model = UniGRModel(UniGRConfig(train_mask_decoder=True, **unigr_config_kwargs())).eval()
+        keys = set(model.model.visual.state_dict().keys())
+        want = {k: v.clone() for k, v in model.model.visual.state_dict().items()}
+        tower = vit.install(model)                       # CPU parameters here: only the swap is exercised, no forward
+        assert {k for k in tower.state_dict().keys()} == {k for k in keys if "inv_freq" not in k}
+        for k, v in tower.state_dict().items():
+            assert torch.equal(v, want[k]), k
+        assert tower.dtype == torch.float32 and tower.spatial_merge_size == 2 and model.model.visual is tower
+    finally:
+        sys.path.remove("/root/reference")
+        if saved is None:
+            sys.modules.pop("qwen_vl_utils", None)
+        else:
+            sys.modules["qwen_vl_utils"] = saved
+        for name in [n for n in sys.modules if n == "model" or n.startswith("model.")]:
+            sys.modules.pop(name, None)
