@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the RGA3 visual path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg4-split]
 
-A step = one pass of the hot path over one synthetic clip of BASELINE config 2
-(16 frames, 448x448, box + mask prompt overlay on every frame, per-frame shift):
-overlay -> normalise -> patchify -> 32-layer Qwen2.5-VL-7B-shaped vision tower ->
-merged visual embeddings [2048, 3584].  N > 1 (torchrun, one rank per GPU): every
-rank processes its own clip per step (weak scaling) and the merged tokens are
-gathered to rank 0 with NCCL inside the timed region.
+A step = one pass of the hot path (STOM overlay -> normalise -> patchify -> 32-layer Qwen2.5-VL-7B-shaped vision tower
+-> merged visual embeddings) over one batch of synthetic input.  Workloads (BASELINE.json `configs`):
+  cfg2 (default, the configuration the metric is quoted on): one 16-frame 448x448 clip per GPU per step, box + mask
+        prompt overlay with a per-frame shift.  Weak scaling: every rank has its own clip.
+  cfg3: a FIXED batch of eight 32-frame 448x448 clips per step, sharded by clip over the ranks (8 / N clips each).
+        Strong scaling.
+  cfg4: one 64-frame 672x672 clip (73,728 patches) per GPU per step.  Weak scaling.
+  cfg4-split: ONE such clip per step, split by temporal slices over the ranks (`shard_slices`: no attention segment
+        spans slices).  Strong scaling.
+For N > 1 (torchrun, one rank per GPU) the merged tokens of every clip go to rank 0 with NCCL inside the timed region.
 
 `value`  : frames/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : same metric through the public module call with HOST (pinned) uint8 frames in
-           and HOST embeddings out, H2D/D2H inside the timed region.
-`--impl reference`: the reference's own CPU implementation of the path (PIL overlay ->
-           HF Qwen2VLVideoProcessor -> HF tower fp32 eager) on this box's host cores, on a
-           bounded sample of the same clip.
+`e2e`    : same metric through the public feed API (ClipPipeline) with HOST (pinned) uint8 frames in and HOST
+           embeddings out, H2D/D2H inside the timed region.
+`cpu_baseline` / `--impl reference`: the reference's own CPU implementation of the path (STOM.warp pixel scatter ->
+           PIL alpha_composite -> HF Qwen2VLVideoProcessor -> HF tower fp32 eager) on this box's host cores, on the
+           whole cfg2 clip.
+`gpu_baseline` (N = 1): the stock GPU path the reference runs (HF tower bf16 + flash-attn-2) on the same box, same run.
 """
 from __future__ import annotations
 
@@ -33,10 +38,19 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-T_FRAMES, H, W = 16, 448, 448
 CFG_7B = dict(depth=32, hidden_size=1280, intermediate_size=3420, num_heads=16, out_hidden_size=3584,
               window_size=112, fullatt_block_indexes=[7, 15, 23, 31])
-WORKLOAD = "cfg2: one 16-frame 448x448 clip, STOM box+mask overlay on all 16 frames, grid_thw=[8,32,32], 8192 patches -> 2048 merged tokens"
+T_FRAMES, H, W = 16, 448, 448   # cfg2
+WORKLOADS = {
+    "cfg2": dict(t=16, hw=448, scaling="weak", desc="cfg2: one 16-frame 448x448 clip, STOM box+mask overlay on all 16 frames, "
+                 "grid_thw=[8,32,32], 8192 patches -> 2048 merged tokens"),
+    "cfg3": dict(t=32, hw=448, scaling="strong", batch=8, desc="cfg3: fixed batch of eight 32-frame 448x448 clips per step "
+                 "(grid_thw=[16,32,32] each, 131072 patches), sharded by clip over the GPUs, STOM overlay on all frames"),
+    "cfg4": dict(t=64, hw=672, scaling="weak", desc="cfg4: one 64-frame 672x672 clip per GPU, grid_thw=[32,48,48], "
+                 "73728 patches -> 18432 merged tokens, STOM overlay on all frames"),
+    "cfg4-split": dict(t=64, hw=672, scaling="strong", split=True, desc="cfg4-split: ONE 64-frame 672x672 clip per step "
+                       "(grid_thw=[32,48,48]) split by temporal slices over the GPUs, STOM overlay on all frames"),
+}
 
 
 # ----------------------------------------------------------------------------- algorithmic work
@@ -71,6 +85,17 @@ def measured_peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, taken from the committed ncu --set full
+    capture named in profiles/traffic.json (not re-measured per run: ncu cannot run inside a timed benchmark)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    j = json.load(open(p))
+    e = j.get(kernel)
+    return (e["bytes_per_launch"], e["source"]) if e else (None, None)
+
+
 # ----------------------------------------------------------------------------- synthetic workload
 def synthetic_frames(t, h, w, clip_id=0):
     g = torch.Generator().manual_seed(1000 + clip_id)
@@ -82,14 +107,22 @@ def synthetic_frames(t, h, w, clip_id=0):
     return ((noise.float() + smooth) * 0.5).round().clamp(0, 255).to(torch.uint8)
 
 
-def prompt_layer():
-    """cfg 2 prompt: red box outline (112,96,335,351) width 4 alpha 200 + lime disc r=80 alpha 100."""
+def prompt_layer(hw=448):
+    """cfg 2 prompt: red box outline (112,96,335,351) width 4 alpha 200 + lime disc r=80 alpha 100 at
+    448x448; scaled with the frame for 672x672."""
     from PIL import Image, ImageDraw
-    vip = Image.new("RGBA", (W, H), (0, 0, 0, 0))
+    s = hw / 448.0
+    vip = Image.new("RGBA", (hw, hw), (0, 0, 0, 0))
     d = ImageDraw.Draw(vip)
-    d.ellipse([(224 - 80, 224 - 80), (224 + 80, 224 + 80)], fill=(0, 255, 0, 100))
-    d.rectangle([(112, 96), (335, 351)], outline=(255, 0, 0, 200), width=4)
+    c, r = int(224 * s), int(80 * s)
+    d.ellipse([(c - r, c - r), (c + r, c + r)], fill=(0, 255, 0, 100))
+    d.rectangle([(int(112 * s), int(96 * s)), (int(335 * s), int(351 * s))], outline=(255, 0, 0, 200), width=max(int(4 * s), 1))
     return np.array(vip)
+
+
+def frame_shifts(t):
+    """per-frame integer translation of the prompt (the output of the STOM policy): dx = dy = frame - t/2, clamped"""
+    return [max(-24, min(24, i - t // 2)) for i in range(t)]
 
 
 def random_state_dict_gpu(tower, seed=0):
@@ -102,7 +135,19 @@ def random_state_dict_gpu(tower, seed=0):
                 p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g, device=p.device))
             else:
                 p.copy_(0.02 * torch.randn(p.shape, generator=g, device=p.device))
-    tower._invalidate()
+    tower.invalidate()
+
+
+def config_dict(workload, world):
+    """The `config` both arms print (the reference arm runs the same workload definition on the host cores)."""
+    wl = WORKLOADS[workload]
+    par = "single GPU" if world == 1 else (
+        f"dp{world}: one clip per GPU, merged tokens gathered to rank 0" if wl["scaling"] == "weak" and not wl.get("split") else
+        f"dp{world}: the step's clips sharded by clip, merged tokens gathered to rank 0" if not wl.get("split") else
+        f"dp{world}: the clip's temporal slices sharded over the GPUs, merged tokens gathered to rank 0")
+    return {"workload": wl["desc"], "weights": "random-init Qwen2.5-VL-7B vision tower shape (676.6M params)",
+            "parallelism": par,
+            "l2": "per-step working set (1.35 GB bf16 weights + >= 0.3 GB activations) exceeds the 126 MB L2; no flush needed"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -172,32 +217,48 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference (CPU) arm
-def reference_step_fn(sample_frames=2):
-    """The reference's CPU path on a bounded sample (first `sample_frames` frames = whole temporal slices, the
-    tower's independent unit): PIL alpha_composite overlay -> HF Qwen2VLVideoProcessor -> HF tower fp32 eager."""
+def reference_step_fn():
+    """The reference's CPU path on the whole cfg2 clip: for every frame STOM.warp's per-pixel scatter of the prompt
+    layer (model/STOM.py:145-155, restated in oracle/overlay_ref.py) -> PIL alpha_composite (:157-160) -> HF
+    Qwen2VLVideoProcessor -> HF tower fp32 eager on all host cores."""
     from PIL import Image
-    from oracle import hf_ref
+    from oracle import hf_ref, overlay_ref
     torch.set_num_threads(os.cpu_count() or 1)
     model, cfg, _ = hf_ref.build_hf_tower(hf_ref.CFG_7B, seed=0, dtype=torch.float32, attn="eager")
-    frames = synthetic_frames(T_FRAMES, H, W, 0)[:sample_frames].numpy()
-    layer = prompt_layer()
+    frames = synthetic_frames(T_FRAMES, H, W, 0).numpy()
+    layer = prompt_layer(H)
+    shifts = frame_shifts(T_FRAMES)
+    parts = {}
 
     def step():
+        t0 = time.perf_counter()
         comp = []
-        for i in range(sample_frames):
-            shifted = np.roll(layer, (i - 8, i - 8), axis=(0, 1))  # integer translate (layer is clear near the border)
-            pil = Image.alpha_composite(Image.fromarray(frames[i], "RGB").convert("RGBA"), Image.fromarray(shifted, "RGBA"))
+        for i in range(T_FRAMES):
+            warped = overlay_ref.warp_layer_ref(layer, float(shifts[i]), float(shifts[i]))
+            pil = Image.alpha_composite(Image.fromarray(frames[i], "RGB").convert("RGBA"), Image.fromarray(warped, "RGBA"))
             comp.append(np.array(pil.convert("RGB")))
+        t1 = time.perf_counter()
         pv, grid = hf_ref.hf_patchify(np.stack(comp))
-        return hf_ref.hf_forward(model, pv, grid)
-    return step, sample_frames
+        t2 = time.perf_counter()
+        out = hf_ref.hf_forward(model, pv, grid)
+        t3 = time.perf_counter()
+        parts.update(overlay_s=t1 - t0, processor_s=t2 - t1, tower_s=t3 - t2)
+        return out
+    return step, T_FRAMES, parts
+
+
+def cpu_baseline_entry(fps, parts, timed_calls):
+    return {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"the whole cfg2 clip (16 frames, grid_thw=[8,32,32]), {timed_calls} timed call(s) after 1 warm-up: STOM.warp "
+                      "pixel scatter + PIL alpha_composite + HF video processor + HF tower fp32 eager on the host cores",
+            "seconds_per_clip": {k: round(v, 3) for k, v in parts.items()}}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    step, nf = reference_step_fn(2)
-    for _ in range(max(args.warmup, 1)):
+    step, nf, parts = reference_step_fn()
+    for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -207,12 +268,43 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "vision_tower_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reference_sample": f"{nf} of 16 frames per step (one temporal slice, grid_thw=[1,32,32])"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "reference",
-                             "sample": f"{nf}-frame slice of the cfg2 clip per step: PIL overlay + HF video processor + HF tower fp32 eager on CPU"},
+            "config": config_dict("cfg2", max(args.gpus, 1)),
+            "cpu_baseline": cpu_baseline_entry(fps, parts, args.steps),
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "tokens_per_s": fps * 128.0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_baseline(dev, pv, grid):
+    """The stock GPU path of the reference (app.py:50-56: bf16, flash_attention_2) on this box: HF tower on the same
+    pixel_values, resident, CUDA-event timed."""
+    from oracle import hf_ref
+    res = {}
+    for attn in ("flash_attention_2", "sdpa"):
+        try:
+            model, _, _ = hf_ref.build_hf_tower(hf_ref.CFG_7B, seed=0, dtype=torch.bfloat16, attn=attn, device=dev)
+            with torch.no_grad():
+                for _ in range(3):
+                    hf_ref.hf_forward(model, pv, grid)
+                torch.cuda.synchronize(dev)
+                ts = []
+                for _ in range(10):
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    hf_ref.hf_forward(model, pv, grid)
+                    e.record()
+                    torch.cuda.synchronize(dev)
+                    ts.append(s.elapsed_time(e))
+            ms = float(np.median(ts))
+            res[attn] = {"ms_per_clip": ms, "frames_per_s": T_FRAMES / (ms * 1e-3)}
+            del model
+            torch.cuda.empty_cache()
+        except Exception as ex:  # flash-attn may be unusable on a box
+            res[attn] = {"error": repr(ex)[:160]}
+    best = min((v["ms_per_clip"], k) for k, v in res.items() if "ms_per_clip" in v) if any("ms_per_clip" in v for v in res.values()) else None
+    return {"what": "HF Qwen2_5_VisionTransformerPretrainedModel bf16 on this GPU, pixel_values resident (overlay / patchify not "
+                    "included), cfg2 clip", "attn": res,
+            "value": (T_FRAMES / (best[0] * 1e-3)) if best else None, "unit": "frames/s", "best_attn": best[1] if best else None}
 
 
 # ----------------------------------------------------------------------------- ours
@@ -222,9 +314,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("BENCH_STREAMS", "1")),
-                    help="clips in flight per GPU (CUDA streams, one workspace each); measured: 2 is 2.7 % slower than 1")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -242,71 +334,68 @@ def main():
     import rga3_release_b200 as vit
     from rga3_release_b200 import _lib
 
+    wl = WORKLOADS[args.workload]
+    t_clip, hw = wl["t"], wl["hw"]
     tower = vit.B200VisionTower(dict(CFG_7B), device=dev, return_dict=False)
     random_state_dict_gpu(tower, seed=0)
-    grid = [[T_FRAMES // 2, H // 14, W // 14]]
-    m = grid[0][0] * grid[0][1] * grid[0][2]
-    layer = prompt_layer()
-    ops = [vit.FrameOp(mode=_lib.FRAME_LAYER, sx=i - 8, sy=i - 8) for i in range(T_FRAMES)]
+
+    # ---- this rank's share of one step: a list of (frames [T,H,W,3], per-frame shifts)
+    layer = prompt_layer(hw)
+    shifts_all = frame_shifts(t_clip)
+    if wl.get("split"):                                   # one clip, contiguous temporal slices per rank
+        t0s, t1s = vit.shard_slices(t_clip // 2, world, rank)
+        clip_ids, f0, f1 = [0], 2 * t0s, 2 * t1s
+    elif "batch" in wl:                                   # fixed batch sharded by clip
+        clip_ids, f0, f1 = vit.shard_clips(wl["batch"], world, rank), 0, t_clip
+    else:                                                 # one clip per rank
+        clip_ids, f0, f1 = [rank], 0, t_clip
+    t_local = f1 - f0
+    frames_per_step_total = (wl["batch"] * t_clip if "batch" in wl else t_clip if wl.get("split") else t_clip * world)
+    clips_host = [synthetic_frames(t_clip, hw, hw, clip_id=c)[f0:f1].contiguous().pin_memory() for c in clip_ids]
+    clips_dev = [c.to(dev) for c in clips_host]
+    ops = [vit.FrameOp(mode=_lib.FRAME_LAYER, sx=s, sy=s) for s in shifts_all[f0:f1]]
     overlay = vit.OverlaySpec.from_rgba(layer, ops, device=dev)
-    frames_host = synthetic_frames(T_FRAMES, H, W, clip_id=rank).pin_memory()
-    frames_dev = frames_host.to(dev)
-    out = torch.empty(m // 4, CFG_7B["out_hidden_size"], dtype=torch.bfloat16, device=dev)
-    outs = [out, torch.empty_like(out)]
-    gather_list = [torch.empty_like(out) for _ in range(world)] if (world > 1 and rank == 0) else None
-    gather_lists = [gather_list, [torch.empty_like(out) for _ in range(world)] if gather_list is not None else None]
-
+    grid = [[t_local // 2, hw // 14, hw // 14]]
+    m = grid[0][0] * grid[0][1] * grid[0][2]
+    n_local = len(clips_dev)
+    rows_per_rank = [((vit.shard_slices(t_clip // 2, world, r)[1] - vit.shard_slices(t_clip // 2, world, r)[0]) * (hw // 28) ** 2
+                      if wl.get("split") else m // 4) for r in range(world)]
+    # two output sets (consecutive steps alternate) so a gather still in flight never aliases the next step's output
+    outs = [[torch.empty(m // 4, CFG_7B["out_hidden_size"], dtype=torch.bfloat16, device=dev) for _ in range(max(n_local, 1))]
+            for _ in range(2)]
+    equal_rows = len(set(rows_per_rank)) == 1
+    gather_lists = [[[torch.empty_like(outs[0][0]) for _ in range(world)] if (world > 1 and rank == 0 and equal_rows) else None
+                     for _ in range(max(n_local, 1))] for _ in range(2)]
     do_gather = world > 1 and not os.environ.get("BENCH_NO_GATHER")
-    gmode = os.environ.get("BENCH_GATHER", "gather")
-    ag_buf = torch.empty(world * out.shape[0], out.shape[1], dtype=out.dtype, device=dev) if world > 1 else None
 
-    def gather_out(t):
-        if gmode == "gather":
-            dist.gather(t, gather_list, dst=0)  # merged tokens -> LLM rank (NCCL over NVLink)
-        elif gmode == "p2p":
-            vit.gather_tokens(t, [t.shape[0]] * world, dst=0)
-        else:
-            dist.all_gather_into_tensor(ag_buf, t)
-
-    pending = [None, None]
+    pending = []
     step_no = [0]
-    n_streams = max(1, min(args.streams, 2))
-    main_stream = torch.cuda.current_stream(dev)
-    side = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else [main_stream]
+
+    def gather_async(t, lst):
+        if equal_rows:
+            return dist.gather(t, lst, dst=0, async_op=True)   # merged tokens -> LLM rank (NCCL over NVLink)
+        vit.gather_tokens(t, rows_per_rank, dst=0)
+        return None
 
     def step_resident():
-        """One clip through the path.  Consecutive clips alternate between `n_streams` CUDA streams (one workspace
-        and one output buffer each), so one clip's kernel tails / set-up overlap the other clip's kernels; with
-        N > 1 the merged tokens go to rank 0 on NCCL's stream while the next clip is already being computed."""
+        """This rank's clips of one step through the path; with N > 1 the merged tokens of each clip go to rank 0 on
+        NCCL's stream while the next clip is already being computed."""
         b = step_no[0] & 1
         step_no[0] += 1
-        st = side[b % n_streams]
-        with torch.cuda.stream(st):
-            if pending[b] is not None:
-                pending[b].wait()          # stream-level wait, the host does not block
-                pending[b] = None
-            tower.forward_frames(frames_dev, overlay, out=outs[b], slot=b % n_streams)
+        while len(pending) > n_local:                     # the set written two steps ago is about to be reused
+            h = pending.pop(0)
+            if h is not None:
+                h.wait()                                  # stream-level wait, the host does not block
+        for ci in range(n_local):
+            tower.forward_frames(clips_dev[ci], overlay, out=outs[b][ci])
             if do_gather:
-                if gmode == "gather":
-                    pending[b] = dist.gather(outs[b], gather_lists[b], dst=0, async_op=True)
-                else:
-                    gather_out(outs[b])
-
-    def fork():
-        for st in side:
-            if st is not main_stream:
-                st.wait_stream(main_stream)
+                pending.append(gather_async(outs[b][ci], gather_lists[b][ci]))
 
     def drain():
-        for b in (0, 1):
-            st = side[b % n_streams]
-            with torch.cuda.stream(st):
-                if pending[b] is not None:
-                    pending[b].wait()
-                    pending[b] = None
-        for st in side:
-            if st is not main_stream:
-                main_stream.wait_stream(st)
+        while pending:
+            h = pending.pop(0)
+            if h is not None:
+                h.wait()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -315,13 +404,11 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- resident-input timing
-    fork()
     for _ in range(args.warmup - 1):
         step_resident()
     drain()
     torch.cuda.synchronize(dev)
     t_w = time.perf_counter()
-    fork()
     step_resident()
     drain()
     torch.cuda.synchronize(dev)
@@ -352,7 +439,6 @@ def main():
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    fork()
     for i in range(args.steps):
         step_resident()
         maybe_probe(i)
@@ -373,7 +459,6 @@ def main():
             sampler.start()
         barrier()
         r_wall0 = time.time()
-        fork()
         for _ in range(min(args.steps, 30)):
             step_resident()
         drain()
@@ -390,18 +475,19 @@ def main():
                                 "(NVML reads inside the NCCL-coupled timed loop inflate the step time, see bench.py)",
                       "nvml_repeat": {k: nv.get(k) for k in ("sm_mhz", "power_w_max", "samples")}}
 
-    # ---- host cost of enqueueing one step: two steps into an empty queue (no back-pressure from the GPU)
+    # ---- host cost of enqueueing one clip: two forwards into an empty queue (no back-pressure from the GPU)
     t_h = time.perf_counter()
     for _ in range(2):
-        tower.forward_frames(frames_dev, overlay, out=out)
+        tower.forward_frames(clips_dev[0], overlay, out=outs[0][0])
     host_ms = (time.perf_counter() - t_h) * 1e3 / 2
     torch.cuda.synchronize(dev)
 
-    # ---- per-kernel breakdown (cudaEvent pairs around every launch; separate pass over the same K steps)
+    # ---- per-kernel breakdown (cudaEvent pairs around every launch; separate pass)
     tower.profile(grid, True)
     kinds = {}
-    for _ in range(args.steps):
-        tower.forward_frames(frames_dev, overlay, out=out)
+    prof_reps = max(1, min(args.steps, 20) // max(n_local, 1))
+    for _ in range(prof_reps):
+        tower.forward_frames(clips_dev[0], overlay, out=outs[0][0])
         for k, (t_ms, n) in tower.profile_read(grid).items():
             a = kinds.setdefault(k, [0.0, 0])
             a[0] += t_ms
@@ -410,77 +496,79 @@ def main():
 
     # ---- end-to-end through the public feed API (rga3_release_b200.ClipPipeline): pinned host uint8 frames in, host
     # embeddings out, H2D / D2H on their own streams, two clips in flight
-    pipe = vit.ClipPipeline(tower, tuple(frames_host.shape), depth=2, to_host=True,
-                            after_forward=(gather_out if do_gather else None))
+    e2e_gather = (lambda t: dist.gather(t, gather_lists[0][0], dst=0)) if (do_gather and equal_rows) else \
+                 ((lambda t: vit.gather_tokens(t, rows_per_rank, dst=0)) if do_gather else None)
+    pipe = vit.ClipPipeline(tower, tuple(clips_host[0].shape), depth=2, to_host=True, after_forward=e2e_gather)
 
     def e2e_loop(n):
         for _ in range(n):
-            pipe.submit(frames_host, overlay)
+            for c in clips_host:
+                pipe.submit(c, overlay)
         pipe.drain()                                   # the last results are in host memory
 
-    e2e_loop(args.warmup)
+    e2e_loop(min(args.warmup, 3))
     barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
+    f0e, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0e.record()
     e2e_loop(args.steps)
-    f1.record()
+    f1e.record()
     barrier()
-    ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    ms2 = torch.tensor([f0e.elapsed_time(f1e)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms_total = float(ms2.item())
 
     if rank == 0:
         peaks = measured_peaks()
-        total_flops, per_flops = algorithmic_flops(grid)
-        frames_total = T_FRAMES * args.steps * world
+        flops_local, per_flops = algorithmic_flops(grid)        # one local clip (or slice range)
+        total_flops_step = algorithmic_flops([[t_clip // 2, hw // 14, hw // 14]])[0] * (frames_per_step_total / t_clip)
+        frames_total = frames_per_step_total * args.steps
         fps = frames_total / (ms_total * 1e-3)
         step_ms = ms_total / args.steps
-        launches = tower.launches_per_forward(grid, with_frames=True)
-        breakdown = {k: round(v[0] / args.steps, 4) for k, v in kinds.items() if v[1]}
+        launches = tower.launches_per_forward(grid, with_frames=True) * n_local
+        breakdown = {k: round(v[0] / prof_reps * n_local, 4) for k, v in kinds.items() if v[1]}   # this GPU's clips of one step
         dom = max((k for k in per_flops if k in kinds and kinds[k][1]), key=lambda k: kinds[k][0])
         dom_ms = kinds[dom][0] / kinds[dom][1]                    # average launch duration
-        dom_flops = per_flops[dom] / (kinds[dom][1] / args.steps)  # algorithmic FLOPs per launch
+        dom_flops = per_flops[dom] / (kinds[dom][1] / prof_reps)  # algorithmic FLOPs per launch
         achieved = dom_flops / (dom_ms * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
+        traffic, traffic_src = measured_traffic(dom) if args.workload == "cfg2" else (None, None)
+        tokens_per_frame = (hw // 28) ** 2 / 2.0
         line = {
             "metric": "vision_tower_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "weights": "random-init Qwen2.5-VL-7B vision tower shape (676.6M params)",
-                       "parallelism": f"clip-sharded dp{world}, merged tokens gathered to rank 0" if world > 1 else "single GPU",
-                       "clips_in_flight_per_gpu": n_streams,
-                       "l2": "per-step working set (1.35 GB bf16 weights + 0.3 GB activations) exceeds the 126 MB L2; no flush needed"},
-            "tokens_per_s": fps * (m // 4) / T_FRAMES,
-            "tower_tflops": total_flops * world / (step_ms * 1e-3) / 1e12,
-            "pct_bf16_peak_burst": total_flops / (step_ms * 1e-3) / 1e12 / peaks["bf16_burst"],
-            "pct_bf16_peak_sustained": total_flops / (step_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "config": config_dict(args.workload, world),
+            "tokens_per_s": fps * tokens_per_frame,
+            "tower_tflops": total_flops_step / (step_ms * 1e-3) / 1e12,
+            "pct_bf16_peak_burst": total_flops_step / world / (step_ms * 1e-3) / 1e12 / peaks["bf16_burst"],
+            "pct_bf16_peak_sustained": total_flops_step / world / (step_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
             "clocks": clocks,
             "e2e": {"value": frames_total / (e2e_ms_total * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
+                    "h2d_bytes_per_step": int(pipe.h2d_bytes) * n_local, "d2h_bytes_per_step": int(pipe.d2h_bytes) * n_local,
                     "ms_per_step": e2e_ms_total / args.steps},
-            "gpu_launches": launches * args.steps, "host_enqueue_ms_per_step": host_ms,
+            "gpu_launches": launches * args.steps, "host_enqueue_ms_per_step": host_ms * n_local,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the ncu --set full
-                         # capture in profiles/r01_ncu_gateup_gemm_full.csv (algorithmic minimum 95 MB: A 21 + W 17.7 +
-                         # out 56.6; part of the output is still in L2 when the kernel ends)
-                         "traffic": 57.4e6 if dom == "gateup_swiglu" else None, "traffic_unit": "bytes/launch",
+                         "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
                          "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                          "flops_per_launch": dom_flops, "avg_launch_ms": dom_ms},
             "kernel_ms_per_step": breakdown,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            stepf, nf = reference_step_fn(2)
+        if world == 1 and args.workload == "cfg2" and not args.no_gpu_baseline:
+            # the same pixels the tower saw, in the HF processor's layout, for the stock GPU path
+            pv = torch.empty(m, 1176, dtype=torch.bfloat16, device=dev)
+            fr = _lib.Frames(clips_dev[0].data_ptr(), t_local, hw, hw)
+            _lib.check(_lib.lib().b200vit_overlay_patchify(fr, overlay.to_c(t_local), 14, 2, 2, pv.data_ptr(),
+                                                           torch.cuda.current_stream(dev).cuda_stream), "overlay_patchify")
+            line["gpu_baseline"] = gpu_baseline(dev, pv, torch.tensor(grid, device=dev))
+        if world == 1 and args.workload == "cfg2" and not args.no_cpu_baseline:
+            stepf, nf, parts = reference_step_fn()
             stepf()
             t0 = time.perf_counter()
-            reps = 2
-            for _ in range(reps):
-                stepf()
-            dt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = {"value": nf / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "reference",
-                                    "sample": f"{nf}-frame slice (grid_thw=[1,32,32]) of the cfg2 clip, {reps} timed calls after 1 warm-up: "
-                                              "PIL overlay + HF video processor + HF tower fp32 eager on the host cores"}
+            stepf()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = cpu_baseline_entry(nf / dt, parts, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
