@@ -21,13 +21,35 @@ MAX_PIXELS = 16384 * 28 * 28
 
 
 def smart_resize(height: int, width: int, factor: int = IMAGE_FACTOR, min_pixels: int = MIN_PIXELS,
-                 max_pixels: int = MAX_PIXELS) -> Tuple[int, int]:
+                 max_pixels: int = MAX_PIXELS, variant: str = "qwen_vl_utils") -> Tuple[int, int]:
     """(h_bar, w_bar): both multiples of ``factor``, pixel count within [min_pixels, max_pixels], aspect ratio kept as
-    closely as possible.  Same rounding as the reference (Python ``round`` is round-half-to-even)."""
+    closely as possible (Python ``round`` is round-half-to-even, as in both sources).
+
+    ``variant="qwen_vl_utils"`` (default) is what the reference runs on every frame: qwen_vl_utils 0.0.10
+    (requirements.txt:16) ``vision_process.smart_resize`` -- the first rounding is floored at ``factor``
+    (``max(factor, round_by_factor(...))``: a side shorter than 14 px does not collapse to 0) and the max_pixels branch
+    is a bare ``floor_by_factor``.  The package is not installed here; restated from its published source.
+    ``variant="transformers"`` is the HF processor's formula (image_processing_qwen2_vl.py:62-89): no floor on the first
+    rounding, ``max(factor, ...)`` in the max_pixels branch.  The two differ only for very small or extreme-aspect
+    frames, e.g. 10 x 1000 -> (28, 1008) vs (28, 560)."""
     if height <= 0 or width <= 0:
         raise ValueError("height and width must be positive")
     if max(height, width) / min(height, width) > 200:
         raise ValueError(f"absolute aspect ratio must be smaller than 200, got {max(height, width) / min(height, width)}")
+    if variant == "qwen_vl_utils":
+        h_bar = max(factor, round(height / factor) * factor)
+        w_bar = max(factor, round(width / factor) * factor)
+        if h_bar * w_bar > max_pixels:
+            beta = math.sqrt((height * width) / max_pixels)
+            h_bar = math.floor(height / beta / factor) * factor
+            w_bar = math.floor(width / beta / factor) * factor
+        elif h_bar * w_bar < min_pixels:
+            beta = math.sqrt(min_pixels / (height * width))
+            h_bar = math.ceil(height * beta / factor) * factor
+            w_bar = math.ceil(width * beta / factor) * factor
+        return h_bar, w_bar
+    if variant != "transformers":
+        raise ValueError("variant must be 'qwen_vl_utils' or 'transformers'")
     h_bar = round(height / factor) * factor
     w_bar = round(width / factor) * factor
     if h_bar * w_bar > max_pixels:

@@ -32,8 +32,20 @@ def test_smart_resize_host_and_oracle(golden_dir):
     import rga3_release_b200 as vit
     rows = np.load(os.path.join(golden_dir, "resize_pil.npz"))["smart_resize"]
     assert len(rows) > 300
+    differ = 0
     for h, w, mn, mp, oh, ow in rows.tolist():
-        assert vit.smart_resize(h, w, 28, mn, mp) == (oh, ow)
+        assert vit.smart_resize(h, w, 28, mn, mp, variant="transformers") == (oh, ow)     # fixture = HF's function
         assert rr.smart_resize_ref(h, w, 28, mn, mp) == (oh, ow)
+        q = vit.smart_resize(h, w, 28, mn, mp)                                            # default: qwen_vl_utils 0.0.10
+        differ += q != (oh, ow)
+        if min(h, w) >= 14 and (oh * ow <= mp):
+            assert q == (oh, ow), (h, w, mn, mp)        # the two sources agree away from tiny sides / the max_pixels floor
+    # known answers of the qwen_vl_utils 0.0.10 rule (what the reference calls, utils/dataset.py:76): the first
+    # rounding is floored at `factor`, so a 10-px side does not push the frame into the min_pixels branch
+    assert vit.smart_resize(10, 1000) == (28, 1008) and vit.smart_resize(10, 1000, variant="transformers") == (28, 560)
+    assert vit.smart_resize(448, 448) == (448, 448) and vit.smart_resize(720, 1280, 28, 3136, 320 * 28 * 28) == (364, 644)
+    assert vit.smart_resize(13, 13) == (56, 56)
     with pytest.raises(ValueError):
         vit.smart_resize(10, 4000)
+    with pytest.raises(ValueError):
+        vit.smart_resize(10, 10, variant="pil")
