@@ -526,6 +526,10 @@ def main():
         fps = frames_total / (ms_total * 1e-3)
         step_ms = ms_total / args.steps
         launches = tower.launches_per_forward(grid, with_frames=True) * n_local
+        if kinds.get("qkv_rope_winattn", [0, 0])[1]:   # windowed layers: projection + window attention in one kernel
+            n_win = CFG_7B["depth"] - len(CFG_7B["fullatt_block_indexes"])
+            per_flops["qkv_rope_winattn"] = per_flops["qkv_rope"] * n_win / CFG_7B["depth"] + per_flops["attn_window"]
+            per_flops["qkv_rope"] *= 1.0 - n_win / CFG_7B["depth"]
         breakdown = {k: round(v[0] / prof_reps * n_local, 4) for k, v in kinds.items() if v[1]}   # this GPU's clips of one step
         dom = max((k for k in per_flops if k in kinds and kinds[k][1]), key=lambda k: kinds[k][0])
         dom_ms = kinds[dom][0] / kinds[dom][1]                    # average launch duration

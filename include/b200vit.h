@@ -95,8 +95,8 @@ size_t b200vit_workspace_bytes(const b200vit_plan* plan);
  * columns of the following weight matrix and rstd is applied per row in that
  * GEMM's epilogue (SURVEY.md 2.1 "RMSNorm x65").                               */
 typedef struct b200vit_layer_weights {
-  const void* qkv_w;        /* bf16 [3D, D], column k scaled by norm1.weight[k]          */
-  const float* qkv_b;       /* [3D]                                                     */
+  const void* qkv_w;        /* bf16 [3D, D], rows head-major [(head, {q,k,v}, head_dim)], column k scaled by norm1.weight[k] */
+  const float* qkv_b;       /* [3D], same row order                                     */
   const void* proj_w;       /* bf16 [D, D]                                              */
   const float* proj_b;      /* [D]                                                      */
   const void* gateup_w;     /* bf16 [2*Ipad, D], rows interleaved g0,u0,g1,u1,...,       */
@@ -134,8 +134,8 @@ typedef struct b200vit_raw_weights {
 /* Packs the raw parameters into one caller-owned DEVICE buffer (256-byte aligned,
  * b200vit_packed_weights_bytes(cfg) bytes) and fills `out` / `out_layers`
  * (HOST array [depth]; out->layers points at it) with pointers into that buffer:
- * bf16 casts, gamma fold of norm1/norm2 into qkv/gate/up, gate/up row interleave,
- * I -> Ipad zero padding.  Work is enqueued on `stream`; host-resident inputs are
+ * bf16 casts, gamma fold of norm1/norm2 into qkv/gate/up, head-major qkv rows, gate/up row
+ * interleave, I -> Ipad zero padding.  Work is enqueued on `stream`; host-resident inputs are
  * staged synchronously.                                                        */
 size_t b200vit_packed_weights_bytes(const b200vit_cfg* cfg);
 int b200vit_pack_weights(const b200vit_cfg* cfg, const b200vit_raw_weights* raw, void* d_packed, size_t packed_bytes,
@@ -200,6 +200,7 @@ int b200vit_forward_launches(const b200vit_plan* plan, int with_frames);
 enum {
   B200VIT_K_OVERLAY_PATCHIFY = 0, B200VIT_K_PATCH_EMBED, B200VIT_K_RMSNORM, B200VIT_K_QKV, B200VIT_K_ATTN_WINDOW,
   B200VIT_K_ATTN_FULL, B200VIT_K_PROJ, B200VIT_K_GATEUP, B200VIT_K_DOWN, B200VIT_K_MERGER_FC1, B200VIT_K_MERGER_FC2,
+  B200VIT_K_QKV_WINATTN, /* QKV projection + RoPE + window attention in one kernel (windowed layers, 64-row windows) */
   B200VIT_K_COUNT
 };
 int b200vit_profile_enable(b200vit_plan* plan, int enable);
@@ -262,14 +263,18 @@ int b200vit_overlay_patchify(const b200vit_frames* frames, const b200vit_overlay
 
 enum {
   B200VIT_EPI_STORE_F32 = 0,     /* out_f32[row_map[r]] = acc                                 */
-  B200VIT_EPI_QKV_ROPE = 1,      /* bf16 out = rope(acc + bias) for cols < 2D, acc + bias after */
+  B200VIT_EPI_QKV_ROPE = 1,      /* B rows head-interleaved [(head, {q,k,v}, 80)] (b200vit_pack_weights); bf16 out [M, 3D] =
+                                    Q | K | V head-major, rope(rstd * acc + bias) for Q and K, rstd * acc + bias for V */
   B200VIT_EPI_BIAS_RESIDUAL = 2, /* out_f32 += acc + bias                                     */
   B200VIT_EPI_SWIGLU = 3,        /* bf16 out[:, c/2] = silu(acc[c]+b[c]) * (acc[c+1]+b[c+1])   */
   B200VIT_EPI_BIAS_GELU = 4,     /* bf16 out = gelu_erf(acc + bias)                           */
   B200VIT_EPI_BIAS_BF16 = 5,     /* bf16 out[row_map[r]] = acc + bias                         */
   B200VIT_EPI_BIAS_F32 = 6,      /* f32  out[row_map[r]] = acc + bias                         */
-  B200VIT_EPI_BIAS_RESIDUAL_NORM = 7 /* out_f32 += acc + bias, and from the NEW out: d_out_bf16 = bf16(out),
+  B200VIT_EPI_BIAS_RESIDUAL_NORM = 7, /* out_f32 += acc + bias, and from the NEW out: d_out_bf16 = bf16(out),
                                     d_rowsq_out partial row sums of out^2 (feeds the next fused RMSNorm) */
+  B200VIT_EPI_QKV_ROPE_WINATTN = 8 /* QKV_ROPE followed, inside the epilogue, by the window attention of HF :244-283 for
+                                    windows of exactly 64 consecutive rows (M % 64 == 0): bf16 out [M, D] = attention
+                                    output, head-major; Q, K, V never leave the SM                                   */
 };
 /* int32 words of the d_sync scratch (zeroed once; every launch leaves it zeroed) */
 #define B200VIT_GEMM_SYNC_INTS 4096
@@ -285,7 +290,6 @@ typedef struct b200vit_gemm_args {
                            with hpos, 20..39 (and 60..79) with wpos                                               */
   int32_t m, n, k;
   int32_t ldo;          /* leading dimension of out, in elements                       */
-  int32_t rope_cols;    /* QKV_ROPE: columns [0, rope_cols) are rotated (= 2D)         */
   int32_t epilogue;     /* B200VIT_EPI_*                                              */
   /* fused RMSNorm (all optional, NULL/0 = off) */
   void* d_out_bf16;        /* STORE_F32 (optional), BIAS_RESIDUAL_NORM (required): bf16 copy of the fp32 output,

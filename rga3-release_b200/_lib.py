@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("B200VIT_LIB") or os.path.join(HERE, "libb200vit.so") 
 
 # epilogues / enums (keep in sync with include/b200vit.h)
 (EPI_STORE_F32, EPI_QKV_ROPE, EPI_BIAS_RESIDUAL, EPI_SWIGLU, EPI_BIAS_GELU, EPI_BIAS_BF16, EPI_BIAS_F32,
- EPI_BIAS_RESIDUAL_NORM) = range(8)
+ EPI_BIAS_RESIDUAL_NORM, EPI_QKV_ROPE_WINATTN) = range(9)
 GEMM_SYNC_INTS = 4096
 VERSION = 3
 LAYER_NONE, LAYER_RGBA, LAYER_PALETTE, LAYER_BOX = range(4)
@@ -68,7 +68,7 @@ class Frames(C.Structure):
 class GemmArgs(C.Structure):
     _fields_ = [("d_a", C.c_void_p), ("d_b", C.c_void_p), ("d_out", C.c_void_p), ("d_bias", C.c_void_p),
                 ("d_row_map", C.c_void_p), ("d_rope", C.c_void_p), ("d_rope_pos", C.c_void_p), ("m", C.c_int32),
-                ("n", C.c_int32), ("k", C.c_int32), ("ldo", C.c_int32), ("rope_cols", C.c_int32),
+                ("n", C.c_int32), ("k", C.c_int32), ("ldo", C.c_int32),
                 ("epilogue", C.c_int32), ("d_out_bf16", C.c_void_p), ("d_rowsq_out", C.c_void_p),
                 ("d_rowsq_in", C.c_void_p), ("rowsq_parts", C.c_int32), ("norm_eps", C.c_float), ("d_sync", C.c_void_p)]
 
@@ -111,7 +111,7 @@ EXPORTS = {
 }
 
 KERNEL_KINDS = ["overlay_patchify", "patch_embed", "rmsnorm", "qkv_rope", "attn_window", "attn_full", "proj_resid",
-                "gateup_swiglu", "down_resid", "merger_fc1", "merger_fc2"]
+                "gateup_swiglu", "down_resid", "merger_fc1", "merger_fc2", "qkv_rope_winattn"]
 
 _lib = None
 

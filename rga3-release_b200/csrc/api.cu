@@ -47,6 +47,7 @@ struct b200vit_plan {
   std::vector<AttnTile> tiles_window, tiles_full;         // tcgen05 attention
   std::vector<int32_t> bounds_window, bounds_full;        // per-row [lo, hi) of the row's segment
   int maxblk_window = 0, maxblk_full = 0;
+  bool uniform_windows = false;  // every window is 64 consecutive rows: the windowed layers' attention runs inside the QKV GEMM
   // workspace layout (byte offsets)
   size_t off_x = 0, off_h = 0, off_qkv = 0, off_attn = 0, off_act = 0, off_pv = 0, off_rowsq = 0, off_sync = 0, ws_bytes = 0;
   int ipad = 0, kpe = 0, rowsq_parts = 0;
@@ -344,6 +345,9 @@ int b200vit_plan_create(const int64_t* h_grid_thw, int n_grids, const b200vit_cf
   build_rope(*p);
   build_attn_tiles(p->cu_window, static_cast<int>(p->m), 128, p->tiles_window, p->bounds_window);
   build_attn_tiles(p->cu_full, static_cast<int>(p->m), 256, p->tiles_full, p->bounds_full);
+  p->uniform_windows = p->m % 64 == 0;
+  for (size_t i = 0; i + 1 < p->cu_window.size() && p->uniform_windows; ++i)
+    p->uniform_windows = p->cu_window[i + 1] - p->cu_window[i] == 64;
   for (const AttnTile& t : p->tiles_window) p->maxblk_window = std::max(p->maxblk_window, t.n_kv_blocks);
   for (const AttnTile& t : p->tiles_full) p->maxblk_full = std::max(p->maxblk_full, t.n_kv_blocks);
   // workspace
@@ -402,10 +406,22 @@ int64_t b200vit_plan_get(const b200vit_plan* p, int which, void* h_dst, size_t c
 
 size_t b200vit_workspace_bytes(const b200vit_plan* p) { return p ? p->ws_bytes : 0; }
 
+static bool fuse_window_attention(const b200vit_plan* p) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VIT_FUSE_WINATTN");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1 && p->uniform_windows && p->cfg.window / p->cfg.merge / p->cfg.patch == 4 && p->unit == 4;
+}
+
 int b200vit_forward_launches(const b200vit_plan* p, int with_frames) {
   if (!p) return 0;
   const int t_pad_windows = 1;  // one overlay/patchify launch per 128 frames; clips here are <= 128 frames
-  return (with_frames ? t_pad_windows : 0) + 1 + p->cfg.depth * 5 + 3;
+  int n_full = 0;
+  for (int l = 0; l < p->cfg.depth; ++l) n_full += is_fullatt(p->cfg, l) ? 1 : 0;
+  const int fused = fuse_window_attention(p) ? p->cfg.depth - n_full : 0;   // those layers have no attention launch
+  return (with_frames ? t_pad_windows : 0) + 1 + p->cfg.depth * 5 - fused + 3;
 }
 
 // The per-workspace memo of this plan (created on first use; at most 8 kept, oldest dropped first).
@@ -452,6 +468,7 @@ int b200vit_forward(const b200vit_plan* p, const b200vit_weights* w, const void*
   int32_t* sync = reinterpret_cast<int32_t*>(ws + p->off_sync);
 
   CallCache* cc = call_cache(p, d_workspace, static_cast<size_t>(3 + 4 * c.depth));
+  const bool fuse_win = fuse_window_attention(p);
   int site = 0;
   Prof prof{cc, stream, p->profile};
   cc->ev_used = 0;
@@ -492,15 +509,21 @@ int b200vit_forward(const b200vit_plan* p, const b200vit_weights* w, const void*
     std::memset(&g, 0, sizeof(g));
     g.d_a = xb, g.d_b = lw.qkv_w, g.d_out = qkv, g.d_bias = lw.qkv_b, g.d_rope = p->d_rope, g.d_rope_pos = p->d_rope_pos;
     g.d_rowsq_in = rowsq, g.rowsq_parts = p->rowsq_parts, g.norm_eps = 1e-6f;
-    g.m = M, g.n = 3 * D, g.k = D, g.ldo = 3 * D, g.rope_cols = 2 * D, g.epilogue = B200VIT_EPI_QKV_ROPE;
-    if ((rc = gemm(B200VIT_K_QKV))) return rc;
-    prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
-    rc = launch_attention_tc(qkv, attn, full ? p->d_tiles_full : p->d_tiles_window,
-                             static_cast<int>(full ? p->tiles_full.size() : p->tiles_window.size()), full ? 256 : 128,
-                             full ? p->maxblk_full : p->maxblk_window, full ? p->d_bounds_full : p->d_bounds_window, M,
-                             c.heads, stream, &cc->attn);
-    if (rc) return rc;
-    prof.end();
+    g.m = M, g.n = 3 * D, g.k = D, g.ldo = 3 * D, g.epilogue = B200VIT_EPI_QKV_ROPE;
+    if (!full && fuse_win) {
+      // windowed layer, every window = 64 consecutive rows: the attention runs inside the QKV epilogue (HF :244-283)
+      g.d_out = attn, g.ldo = D, g.epilogue = B200VIT_EPI_QKV_ROPE_WINATTN;
+      if ((rc = gemm(B200VIT_K_QKV_WINATTN))) return rc;
+    } else {
+      if ((rc = gemm(B200VIT_K_QKV))) return rc;
+      prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
+      rc = launch_attention_tc(qkv, attn, full ? p->d_tiles_full : p->d_tiles_window,
+                               static_cast<int>(full ? p->tiles_full.size() : p->tiles_window.size()), full ? 256 : 128,
+                               full ? p->maxblk_full : p->maxblk_window, full ? p->d_bounds_full : p->d_bounds_window, M,
+                               c.heads, stream, &cc->attn);
+      if (rc) return rc;
+      prof.end();
+    }
     // x += attn Wp^T + b; xb = bf16(x); rowsq = partial row sums of x^2                            (HF :313-316)
     std::memset(&g, 0, sizeof(g));
     g.d_a = attn, g.d_b = lw.proj_w, g.d_out = x, g.d_bias = lw.proj_b;

@@ -47,7 +47,7 @@ struct GemmParams {
   const int32_t* row_map;
   const float2* rope;     // [P, 20] fp32 (cos, sin) of coordinate * inv_freq, P = largest grid side
   const int2* rope_pos;   // [M] (hpos, wpos) of every row
-  int m, n, k, ldo, rope_cols;
+  int m, n, k, ldo;
   int stream_k;  // bit 0: stream-K decomposition (BIAS_RESIDUAL_NORM only); bit 1: no weight prefetch before the PDL wait
   // fused RMSNorm (HF :57-71): RMSNorm(x) W^T == rstd(x) * (x (W diag(gamma))^T).  Producers of the fp32 residual
   // stream also emit its bf16 copy (the next GEMM's A operand) and per-row partial sums of x^2, one per 128-column
@@ -84,7 +84,8 @@ __host__ __device__ constexpr bool is_resid_norm(int epi) { return epi == B200VI
 constexpr int RESID_BUFS = B200_RESID_BUFS;  // staging buffers per warp of the reduce-add epilogue
 // staging bytes per epilogue warp (TMA-store epilogues), 0 = direct global stores
 __host__ __device__ constexpr int epi_stage_bytes(int epi) {
-  return epi == B200VIT_EPI_QKV_ROPE        ? 32 * 160
+  return epi == B200VIT_EPI_QKV_ROPE_WINATTN ? 32 * 176  // padded rows: conflict-free ldmatrix of the staged Q, K, V
+         : epi == B200VIT_EPI_QKV_ROPE      ? 32 * 160
          : epi == B200VIT_EPI_BIAS_RESIDUAL ? RESID_BUFS * 4096
          : is_resid_norm(epi) ? 4096  // one 32 x 32 fp32 chunk of (acc + bias) in transit between the two thread layouts
          : epi == B200VIT_EPI_SWIGLU        ? 4096
@@ -101,7 +102,9 @@ struct TileCfg {
   static constexpr int B_BYTES = BN_LOAD * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 4 * EG;
-  static constexpr int STG_WARP = (epi_stage_bytes(EPI) + 1023) / 1024 * 1024;
+  // swizzled TMA staging wants 1024-byte alignment; the fused-attention staging is only read by ldmatrix / a dense
+  // TMA box (128-byte alignment) and keeps its exact size so that five operand stages still fit
+  static constexpr int STG_WARP = EPI == B200VIT_EPI_QKV_ROPE_WINATTN ? epi_stage_bytes(EPI) : (epi_stage_bytes(EPI) + 1023) / 1024 * 1024;
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
   static constexpr int BAR_BYTES = 256;
   static constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - STG_BYTES;
@@ -120,6 +123,65 @@ __device__ __forceinline__ float4 bias4(const float* bias, int col, int n) {
   return (col + 4 <= n) ? ldg4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// One row of one head of Q, K or V: rstd * acc + bias, 2-D RoPE for Q and K (HF :149-167), bf16, 160 bytes at `srow`.
+// `rs` = fused RMSNorm: per-row rstd of the A operand's source.  `bcol` = first of the head's 80 bias entries.
+__device__ __forceinline__ void qkv_row_to_smem(uint32_t taddr, int row, bool row_ok, int bcol, bool rope, const GemmParams& p,
+                                                float rs, uint32_t srow) {
+  if (rope) {
+    // HF :382-409: rotary_pos_emb = freqs[pos_ids] with freqs = outer(arange(max_grid), inv_freq): dims 0..19 turn
+    // with the row's hpos, dims 20..39 with its wpos.  The [P, 20] table stays in L1; only 8 bytes per row are new.
+    const int2 pos = row_ok ? __ldg(p.rope_pos + row) : make_int2(0, 0);
+    const float4* th = reinterpret_cast<const float4*>(p.rope + static_cast<size_t>(pos.x) * 20);
+    const float4* tv = reinterpret_cast<const float4*>(p.rope + static_cast<size_t>(pos.y) * 20);
+#pragma unroll
+    for (int d0 = 0; d0 < 40; d0 += 8) {
+      uint32_t lo[8], hi[8];
+      tmem_ld8(taddr + d0, lo);
+      tmem_ld8(taddr + 40 + d0, hi);
+      float4 tw[4];  // (cos, sin) pairs of dims d0 .. d0+7, fp32 as HF rotates (:149-167)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = d0 + 2 * i;
+        tw[i] = d < 20 ? __ldg(th + (d >> 1)) : __ldg(tv + ((d - 20) >> 1));
+      }
+      float bl[8], bh[8];
+      *reinterpret_cast<float4*>(&bl[0]) = ldg4(p.bias + bcol + d0);
+      *reinterpret_cast<float4*>(&bl[4]) = ldg4(p.bias + bcol + d0 + 4);
+      *reinterpret_cast<float4*>(&bh[0]) = ldg4(p.bias + bcol + 40 + d0);
+      *reinterpret_cast<float4*>(&bh[4]) = ldg4(p.bias + bcol + 40 + d0 + 4);
+      tmem_ld_wait();
+      uint32_t olo[4], ohi[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float c0 = tw[j >> 1].x, s0 = tw[j >> 1].y, c1 = tw[j >> 1].z, s1 = tw[j >> 1].w;
+        const float x0 = __uint_as_float(lo[j]) * rs + bl[j], x1 = __uint_as_float(lo[j + 1]) * rs + bl[j + 1];
+        const float y0 = __uint_as_float(hi[j]) * rs + bh[j], y1 = __uint_as_float(hi[j + 1]) * rs + bh[j + 1];
+        // rotate_half: out[d] = x*cos - y*sin ; out[d+40] = y*cos + x*sin
+        olo[j >> 1] = pack_bf16x2(x0 * c0 - y0 * s0, x1 * c1 - y1 * s1);
+        ohi[j >> 1] = pack_bf16x2(y0 * c0 + x0 * s0, y1 * c1 + x1 * s1);
+      }
+      st_shared_v4(srow + d0 * 2, olo[0], olo[1], olo[2], olo[3]);
+      st_shared_v4(srow + 80 + d0 * 2, ohi[0], ohi[1], ohi[2], ohi[3]);
+    }
+  } else {
+#pragma unroll
+    for (int d0 = 0; d0 < 80; d0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + d0, v);
+      tmem_ld_wait();
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = ldg4(p.bias + bcol + d0 + j);
+        o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * rs + b.x, __uint_as_float(v[j + 1]) * rs + b.y);
+        o[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) * rs + b.z, __uint_as_float(v[j + 3]) * rs + b.w);
+      }
+      st_shared_v4(srow + d0 * 2, o[0], o[1], o[2], o[3]);
+      st_shared_v4(srow + d0 * 2 + 16, o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ epilogues
 // Each epilogue thread owns one accumulator row (TMEM lane) and CW consecutive columns.
 // `stg` = this warp's staging buffer (shared address), `row0` = first row of the warp's 32-row slab.
@@ -132,65 +194,13 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
     static_assert(CW == 80, "QKV epilogue handles one 80-wide head per warp group");
     if (lane == 0) bulk_wait_read<0>();  // previous tile's store has drained the staging buffer
     __syncwarp();
-    const uint32_t srow = stg + lane * 160;
-    // `rs` = fused RMSNorm: per-row rstd of the A operand's source
-    if (col0 < p.rope_cols) {
-      // HF :382-409: rotary_pos_emb = freqs[pos_ids] with freqs = outer(arange(max_grid), inv_freq): dims 0..19 turn
-      // with the row's hpos, dims 20..39 with its wpos.  The [P, 20] table stays in L1; only 8 bytes per row are new.
-      const int2 pos = row_ok ? __ldg(p.rope_pos + row) : make_int2(0, 0);
-      const float4* th = reinterpret_cast<const float4*>(p.rope + static_cast<size_t>(pos.x) * 20);
-      const float4* tv = reinterpret_cast<const float4*>(p.rope + static_cast<size_t>(pos.y) * 20);
-#pragma unroll
-      for (int d0 = 0; d0 < 40; d0 += 8) {
-        uint32_t lo[8], hi[8];
-        tmem_ld8(taddr + d0, lo);
-        tmem_ld8(taddr + 40 + d0, hi);
-        float4 tw[4];  // (cos, sin) pairs of dims d0 .. d0+7, fp32 as HF rotates (:149-167)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int d = d0 + 2 * i;
-          tw[i] = d < 20 ? __ldg(th + (d >> 1)) : __ldg(tv + ((d - 20) >> 1));
-        }
-        float bl[8], bh[8];
-        *reinterpret_cast<float4*>(&bl[0]) = ldg4(p.bias + col0 + d0);
-        *reinterpret_cast<float4*>(&bl[4]) = ldg4(p.bias + col0 + d0 + 4);
-        *reinterpret_cast<float4*>(&bh[0]) = ldg4(p.bias + col0 + 40 + d0);
-        *reinterpret_cast<float4*>(&bh[4]) = ldg4(p.bias + col0 + 40 + d0 + 4);
-        tmem_ld_wait();
-        uint32_t olo[4], ohi[4];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const float c0 = tw[j >> 1].x, s0 = tw[j >> 1].y, c1 = tw[j >> 1].z, s1 = tw[j >> 1].w;
-          const float x0 = __uint_as_float(lo[j]) * rs + bl[j], x1 = __uint_as_float(lo[j + 1]) * rs + bl[j + 1];
-          const float y0 = __uint_as_float(hi[j]) * rs + bh[j], y1 = __uint_as_float(hi[j + 1]) * rs + bh[j + 1];
-          // rotate_half: out[d] = x*cos - y*sin ; out[d+40] = y*cos + x*sin   (HF :149-167)
-          olo[j >> 1] = pack_bf16x2(x0 * c0 - y0 * s0, x1 * c1 - y1 * s1);
-          ohi[j >> 1] = pack_bf16x2(y0 * c0 + x0 * s0, y1 * c1 + x1 * s1);
-        }
-        st_shared_v4(srow + d0 * 2, olo[0], olo[1], olo[2], olo[3]);
-        st_shared_v4(srow + 80 + d0 * 2, ohi[0], ohi[1], ohi[2], ohi[3]);
-      }
-    } else {
-#pragma unroll
-      for (int d0 = 0; d0 < 80; d0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + d0, v);
-        tmem_ld_wait();
-        uint32_t o[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b = ldg4(p.bias + col0 + d0 + j);
-          o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * rs + b.x, __uint_as_float(v[j + 1]) * rs + b.y);
-          o[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) * rs + b.z, __uint_as_float(v[j + 3]) * rs + b.w);
-        }
-        st_shared_v4(srow + d0 * 2, o[0], o[1], o[2], o[3]);
-        st_shared_v4(srow + d0 * 2 + 16, o[4], o[5], o[6], o[7]);
-      }
-    }
+    // weight rows are head-interleaved [(head, {q, k, v}, 80)]: tile column col0 = head * 240 + type * 80
+    const int head = col0 / 240, type = (col0 % 240) / 80;
+    qkv_row_to_smem(taddr, row_ok ? row : 0, row_ok, col0, type < 2, p, rs, stg + lane * 160);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tma_out, stg, col0, row0);
+      tma_store_2d(tma_out, stg, type * (p.n / 3) + head * 80, row0);  // the qkv buffer stays Q | K | V, head-major
       bulk_commit();
     }
   } else if constexpr (EPI == B200VIT_EPI_BIAS_RESIDUAL) {
@@ -446,7 +456,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   }
   tc_fence_before();
-  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if constexpr (PAIR) {
+    cluster_sync_all();
+    __syncthreads();  // redundant after the cluster barrier; lets compute-sanitizer racecheck see the ordering of tmem_slot
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  Each role executes
@@ -587,6 +602,128 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #else
 #define ESTAMP(v)
 #endif
+    if constexpr (EPI == B200VIT_EPI_QKV_ROPE_WINATTN) {
+      // QKV projection + RoPE + the WINDOW attention of the 28 windowed layers in one kernel.  The weight rows are
+      // head-interleaved, so the 240 columns of a tile are Q_h | K_h | V_h of one head h, and a CTA's 128 rows are two
+      // 64-patch windows: everything softmax(Q K^T / sqrt(80)) V needs for (2 windows x 1 head) is in this CTA's
+      // accumulator.  The 12 epilogue warps stage Q, K (rotated) and V as bf16 in shared memory exactly as the plain
+      // epilogue does -- and then, instead of storing them, eight warps run the attention of 16 query rows each with
+      // warp-level MMAs (5.2 MFLOP per tile against 78.6 MFLOP of projection) and store the 16 x 80 output rows.
+      // Q, K, V never reach L2 / HBM (63 MB written and read back per layer otherwise) and the 28 attention launches
+      // disappear.  Overlaps the next tile's main loop like every other epilogue.
+      static_assert(CW == 80 && EG == 3, "one head per tile: Q | K | V groups of 80 columns");
+      constexpr int RS = 176;  // staged row stride in bytes
+      constexpr int EPI_THREADS = 128 * EG;
+      const uint32_t stg_all = smem_u32(sStg);
+      const float scale_log2 = 0.11180339887498948f * 1.4426950408889634f;  // 80^-0.5 * log2(e)
+      for (; work.next(sg); ++it) {
+        const int m0 = (sg.tile / num_n) * MT + rank * BM;
+        const int head = sg.tile % num_n;
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        const int row = m0 + q * 32 + lane;
+        const float rs = row_rstd(p, row < p.m ? row : 0);
+        ESTAMP(e_busy);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        ESTAMP(e_wait);
+        const uint32_t taddr = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16) + g * CW;
+        if (lane == 0) bulk_wait_read<0>();  // the previous tile's output store has drained this warp's buffer
+        __syncwarp();
+        qkv_row_to_smem(taddr, row < p.m ? row : 0, row < p.m, head * 240 + g * 80, g < 2, p, rs, stg + lane * RS);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+          else mbar_arrive(&tempty[as]);
+        }
+        named_barrier(1, EPI_THREADS);  // Q, K, V of the CTA's two windows are staged
+        uint32_t opk[20];               // this warp's 16 x 80 output, bf16 pairs: [dim tile][row half]
+        if (g < 2) {
+          const int w = q >> 1;         // window (rows 64 w .. 64 w + 63 of the CTA) of this warp's 16 query rows
+          const uint32_t qb = stg_all + (0 * 4 + q) * C::STG_WARP + (16 * g) * RS;
+          const int lr = (lane & 7) + 8 * ((lane >> 3) & 1), lc = lane >> 4;     // ldmatrix address roles
+          float sacc[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks) {  // S = Q K^T over the 80 head dims, 16 at a time
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(qb + lr * RS + (ks * 16 + 8 * lc) * 2, a0, a1, a2, a3);
+#pragma unroll
+            for (int nt = 0; nt < 8; nt += 2) {  // keys 8 nt .. 8 nt + 15
+              const uint32_t kb = stg_all + (1 * 4 + 2 * w + (nt >> 2)) * C::STG_WARP + ((8 * nt) & 31) * RS;
+              uint32_t b0, b1, b2, b3;
+              ldmatrix_x4(kb + ((lane & 7) + 8 * lc) * RS + (ks * 16 + 8 * ((lane >> 3) & 1)) * 2, b0, b1, b2, b3);
+              mma_bf16_16816(sacc[nt], a0, a1, a2, a3, b0, b1);
+              mma_bf16_16816(sacc[nt + 1], a0, a1, a2, a3, b2, b3);
+            }
+          }
+          // softmax over the window's 64 keys; a thread holds rows lane/4 and lane/4 + 8, a quad holds a whole row
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            mx0 = fmaxf(mx0, fmaxf(sacc[i][0], sacc[i][1]));
+            mx1 = fmaxf(mx1, fmaxf(sacc[i][2], sacc[i][3]));
+          }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          float sum0 = 0.f, sum1 = 0.f;
+          uint32_t pa[4][4];  // P as A operands of the four 16-key steps
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e0 = ex2f((sacc[i][0] - mx0) * scale_log2), e1 = ex2f((sacc[i][1] - mx0) * scale_log2);
+            const float e2 = ex2f((sacc[i][2] - mx1) * scale_log2), e3 = ex2f((sacc[i][3] - mx1) * scale_log2);
+            sum0 += e0 + e1, sum1 += e2 + e3;
+            pa[i >> 1][(i & 1) * 2] = pack_bf16x2(e0, e1);
+            pa[i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(e2, e3);
+          }
+          sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1), sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+          sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1), sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+          const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {  // O = P V, 40 of the 80 dims per pass (register pressure)
+            float oacc[5][4];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // keys 16 j .. 16 j + 15
+              const uint32_t vb = stg_all + (2 * 4 + 2 * w + (j >> 1)) * C::STG_WARP + ((16 * j) & 31) * RS;
+#pragma unroll
+              for (int dt = 0; dt < 5; dt += 2) {
+                uint32_t b0, b1, b2, b3;
+                // the fifth dim tile of a pass has no partner: its second half re-reads a valid neighbour and is unused
+                const int d0 = half * 40 + dt * 8, dsec = dt + 1 < 5 ? 8 * lc : 0;
+                ldmatrix_x4_trans(vb + lr * RS + (d0 + dsec) * 2, b0, b1, b2, b3);
+                mma_bf16_16816(oacc[dt], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b0, b1);
+                if (dt + 1 < 5) mma_bf16_16816(oacc[dt + 1], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b2, b3);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              opk[(half * 5 + i) * 2] = pack_bf16x2(oacc[i][0] * inv0, oacc[i][1] * inv0);
+              opk[(half * 5 + i) * 2 + 1] = pack_bf16x2(oacc[i][2] * inv1, oacc[i][3] * inv1);
+            }
+          }
+        }
+        named_barrier(2, EPI_THREADS);  // every read of the staged Q, K, V is done: the buffers may be reused
+        if (g < 2) {
+          // 16 x 80 bf16, dense 160-byte rows at the start of this warp's own buffer -> one TMA store
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            const uint32_t base = stg + (i * 8 + 2 * (lane & 3)) * 2;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (lane >> 2) * 160), "r"(opk[2 * i]) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + ((lane >> 2) + 8) * 160), "r"(opk[2 * i + 1]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_out, stg, head * 80, m0 + q * 32 + 16 * g);
+            bulk_commit();
+          }
+        }
+      }
+    } else
     if constexpr (is_resid_norm(EPI)) {
       // x += acc + bias with the NEW x in hand: besides the fp32 residual stream the epilogue writes its bf16 copy
       // (A operand of the next GEMM) and per-row sums of squares (the next RMSNorm's statistics).
@@ -808,6 +945,8 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     g.taux = g.ta;
     if (is_resid_norm(EPI)) {
       rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, 128);  // reduce-add of stream-K tail partials
+    } else if (EPI == B200VIT_EPI_QKV_ROPE_WINATTN) {
+      rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 3, a.ldo, 2, 16, 80, 0);  // attention output [M, D], 16-row boxes
     } else if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, 0);
     else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, 128);
     else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, 128);
@@ -840,7 +979,7 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
   }
   GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const float2*>(a.d_rope),
                reinterpret_cast<const int2*>(a.d_rope_pos), a.m, a.n, a.k, a.ldo,
-               a.rope_cols, g.stream_k | (weight_prefetch_enabled() ? 0 : 2),
+               g.stream_k | (weight_prefetch_enabled() ? 0 : 2),
                reinterpret_cast<__nv_bfloat16*>(a.d_out_bf16), a.d_rowsq_out, a.d_rowsq_in, a.rowsq_parts, a.norm_eps, a.d_sync};
   auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
   static DeviceOnce attr_set;  // per instantiation and device
@@ -868,7 +1007,8 @@ int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* c
   const bool needs_bias = a.epilogue != B200VIT_EPI_STORE_F32;
   if (a.d_rowsq_in != nullptr && (a.rowsq_parts <= 0 || a.rowsq_parts > MAX_ROWSQ_PARTS))
     return fail(B200VIT_EINVAL, "gemm: d_rowsq_in needs 1 <= rowsq_parts <= 16 (K <= 2048)");
-  if (a.d_rowsq_in != nullptr && a.epilogue != B200VIT_EPI_QKV_ROPE && a.epilogue != B200VIT_EPI_SWIGLU)
+  if (a.d_rowsq_in != nullptr && a.epilogue != B200VIT_EPI_QKV_ROPE && a.epilogue != B200VIT_EPI_SWIGLU &&
+      a.epilogue != B200VIT_EPI_QKV_ROPE_WINATTN)
     return fail(B200VIT_EINVAL, "gemm: d_rowsq_in (fused RMSNorm) is implemented by the QKV_ROPE and SWIGLU epilogues");
   if ((a.d_out_bf16 != nullptr || a.d_rowsq_out != nullptr) && a.epilogue != B200VIT_EPI_STORE_F32 &&
       a.epilogue != B200VIT_EPI_BIAS_RESIDUAL_NORM)
@@ -882,10 +1022,15 @@ int launch_gemm(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* c
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
       return launch_one<256, 2, B200VIT_EPI_BIAS_F32>(a, stream, cache);
     case B200VIT_EPI_QKV_ROPE:
-      if (a.n % 240 || a.rope_cols % 80 || a.ldo % 8 || !a.d_rope || !a.d_rope_pos ||
+      if (a.n % 240 || a.ldo % 8 || !a.d_rope || !a.d_rope_pos ||
           ((reinterpret_cast<uintptr_t>(a.d_rope) | reinterpret_cast<uintptr_t>(a.d_rope_pos)) & 15))
         return fail(B200VIT_EINVAL, "gemm: QKV epilogue needs N % 240 == 0, head_dim 80, a 16-byte aligned rope table and row positions");
       return launch_one<240, 3, B200VIT_EPI_QKV_ROPE>(a, stream, cache);
+    case B200VIT_EPI_QKV_ROPE_WINATTN:
+      if (a.n % 240 || a.ldo % 8 || a.m % 64 || !a.d_rope || !a.d_rope_pos ||
+          ((reinterpret_cast<uintptr_t>(a.d_rope) | reinterpret_cast<uintptr_t>(a.d_rope_pos)) & 15))
+        return fail(B200VIT_EINVAL, "gemm: fused window attention needs N % 240 == 0, head_dim 80, M % 64 == 0, a rope table and row positions");
+      return launch_one<240, 3, B200VIT_EPI_QKV_ROPE_WINATTN>(a, stream, cache);
     case B200VIT_EPI_BIAS_RESIDUAL:
       if (a.n % 8 || a.ldo % 4) return fail(B200VIT_EINVAL, "gemm: N % 8 and ldo % 4 required");
       return launch_one<256, 2, B200VIT_EPI_BIAS_RESIDUAL>(a, stream, cache);

@@ -41,6 +41,29 @@ pack_matrix_kernel(const T* __restrict__ src, int64_t rows, int64_t cols, const 
   }
 }
 
+// qkv projection: HF rows are type-major [q heads | k heads | v heads]; the kernels want them head-major
+// [(head, {q, k, v}, head_dim)] so that one 240-column GEMM tile holds Q_h | K_h | V_h of one head (the fused
+// window-attention epilogue needs all three in one accumulator).  `cols` = 0 packs the bias vector the same way.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_qkv_kernel(const T* __restrict__ src, int64_t d_model, int64_t cols, int head_dim, const T* __restrict__ gamma,
+                __nv_bfloat16* __restrict__ dst_w, float* __restrict__ dst_b) {
+  const int64_t width = cols > 0 ? cols : 1;
+  const int64_t n = 3 * d_model * width;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / width, c = i - r * width;          // destination row: (h * 3 + t) * head_dim + d
+    const int64_t h = r / (3 * head_dim), t = (r / head_dim) % 3, d = r % head_dim;
+    const int64_t sr = t * d_model + h * head_dim + d;
+    if (cols > 0) {
+      float v = as_f32<T>(src[sr * cols + c]);
+      if (gamma != nullptr) v *= as_f32<T>(gamma[c]);
+      dst_w[i] = __float2bfloat16_rn(v);
+    } else {
+      dst_b[r] = as_f32<T>(src[sr]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_vector_kernel(const T* __restrict__ src, int64_t n, float* __restrict__ dst, int mul, int off) {
@@ -107,6 +130,26 @@ struct Packer {
     B200_CUDA_OK(cudaGetLastError());
     return 0;
   }
+  // head-interleaved qkv weight ([3D, D] with gamma folded) or, with cols = 0, bias ([3D])
+  int qkv(const void* src, int64_t d_model, int64_t cols, int head_dim, const void* gamma, void* dst) {
+    if (!src) return fail(B200VIT_EINVAL, "pack_weights: null tensor");
+    const void *s = nullptr, *g = nullptr;
+    int rc;
+    if ((rc = st.view(src, 3 * d_model * (cols > 0 ? cols : 1), 0, &s))) return rc;
+    if (gamma && (rc = st.view(gamma, cols, 1, &g))) return rc;
+    const int64_t n = 3 * d_model * (cols > 0 ? cols : 1);
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 16));
+    __nv_bfloat16* dw = reinterpret_cast<__nv_bfloat16*>(dst);
+    float* db = reinterpret_cast<float*>(dst);
+    if (st.dtype == 0)
+      pack_qkv_kernel<float><<<grid, 256, 0, st.stream>>>(reinterpret_cast<const float*>(s), d_model, cols, head_dim, reinterpret_cast<const float*>(g), dw, db);
+    else if (st.dtype == 1)
+      pack_qkv_kernel<__half><<<grid, 256, 0, st.stream>>>(reinterpret_cast<const __half*>(s), d_model, cols, head_dim, reinterpret_cast<const __half*>(g), dw, db);
+    else
+      pack_qkv_kernel<__nv_bfloat16><<<grid, 256, 0, st.stream>>>(reinterpret_cast<const __nv_bfloat16*>(s), d_model, cols, head_dim, reinterpret_cast<const __nv_bfloat16*>(g), dw, db);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   int vector(const void* src, int64_t n, void* dst, int mul, int off) {
     if (!src) return fail(B200VIT_EINVAL, "pack_weights: null tensor");
     const void* s = nullptr;
@@ -167,6 +210,8 @@ extern "C" int b200vit_pack_weights(const b200vit_cfg* cfg, const b200vit_raw_we
     return p;
   };
   const int64_t d = L.d, i = L.i, ipad = L.ipad, o = L.o, ud = L.u * L.d;
+  if (cfg->heads <= 0 || cfg->hidden % cfg->heads) return fail(B200VIT_EINVAL, "pack_weights: bad hidden/heads");
+  const int head_dim = cfg->hidden / cfg->heads;
   int rc;
   void* p;
   p = take(L.d * L.kpe * 2);
@@ -176,10 +221,10 @@ extern "C" int b200vit_pack_weights(const b200vit_cfg* cfg, const b200vit_raw_we
     const b200vit_raw_layer& r = raw->layers[l];
     b200vit_layer_weights& w = out_layers[l];
     p = take(3 * L.d * L.d * 2);
-    if ((rc = pk.matrix(r.qkv_w, 3 * d, d, r.norm1_w, p, d, 1, 0))) return rc;
+    if ((rc = pk.qkv(r.qkv_w, d, d, head_dim, r.norm1_w, p))) return rc;
     w.qkv_w = p;
     p = take(3 * L.d * 4);
-    if ((rc = pk.vector(r.qkv_b, 3 * d, p, 1, 0))) return rc;
+    if ((rc = pk.qkv(r.qkv_b, d, 0, head_dim, nullptr, p))) return rc;
     w.qkv_b = reinterpret_cast<const float*>(p);
     p = take(L.d * L.d * 2);
     if ((rc = pk.matrix(r.proj_w, d, d, nullptr, p, d, 1, 0))) return rc;

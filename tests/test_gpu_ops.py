@@ -31,7 +31,7 @@ def make_rope(m, seed, side=50):
     return (table.to(DEV), pos.to(DEV)), full.cos(), full.sin()
 
 
-def run_gemm(a, b, epi, out, bias=None, row_map=None, rope=None, ldo=None, rope_cols=0, out_bf16=None, rowsq_out=None,
+def run_gemm(a, b, epi, out, bias=None, row_map=None, rope=None, ldo=None, out_bf16=None, rowsq_out=None,
              rowsq_in=None, eps=1e-6, sync=None):
     g = _lib.GemmArgs()
     g.d_a, g.d_b, g.d_out = a.data_ptr(), b.data_ptr(), out.data_ptr()
@@ -42,7 +42,6 @@ def run_gemm(a, b, epi, out, bias=None, row_map=None, rope=None, ldo=None, rope_
     g.m, g.k = a.shape
     g.n = b.shape[0]
     g.ldo = ldo if ldo is not None else out.shape[1]
-    g.rope_cols = rope_cols
     g.epilogue = epi
     g.d_out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
     g.d_rowsq_out = rowsq_out.data_ptr() if rowsq_out is not None else None
@@ -51,6 +50,13 @@ def run_gemm(a, b, epi, out, bias=None, row_map=None, rope=None, ldo=None, rope_
     g.d_sync = sync.data_ptr() if sync is not None else None
     _lib.check(_lib.lib().b200vit_gemm(C.byref(g), _stream()), "gemm")
     torch.cuda.synchronize()
+
+
+def head_major(w, d):
+    """HF qkv rows [q heads | k heads | v heads] -> the kernels' head-major order [(head, {q,k,v}, 80)]
+    (what b200vit_pack_weights does to attn.qkv.weight / bias)."""
+    nh = d // 80
+    return w.reshape(3, nh, 80, *w.shape[1:]).transpose(0, 1).reshape(w.shape).contiguous()
 
 
 def rowsq_parts(x):
@@ -104,7 +110,7 @@ def test_gemm_qkv_rope(m, d):
     bias = rnd((3 * d,), 6, 0.1, torch.float32)
     rope, cos, sin = make_rope(m, 7)
     out = torch.zeros(m, 3 * d, dtype=torch.bfloat16, device=DEV)
-    run_gemm(a, b, _lib.EPI_QKV_ROPE, out, bias=bias, rope=rope, rope_cols=2 * d)
+    run_gemm(a, head_major(b, d), _lib.EPI_QKV_ROPE, out, bias=head_major(bias, d), rope=rope)
     qkv = (a.float() @ b.float().t() + bias).cpu().reshape(m, 3, nh, 80)
     c80 = torch.cat([cos, cos], -1).cpu()
     s80 = torch.cat([sin, sin], -1).cpu()
@@ -183,7 +189,8 @@ def test_gemm_fused_rmsnorm_consumers():
     bias = rnd((3 * d,), 23, 0.1, torch.float32)
     rope, cos, sin = make_rope(m, 24)
     out = torch.zeros(m, 3 * d, dtype=torch.bfloat16, device=DEV)
-    run_gemm(xb, (w * gamma).to(torch.bfloat16), _lib.EPI_QKV_ROPE, out, bias=bias, rope=rope, rope_cols=2 * d, rowsq_in=rs_in)
+    run_gemm(xb, head_major((w * gamma).to(torch.bfloat16), d), _lib.EPI_QKV_ROPE, out, bias=head_major(bias, d), rope=rope,
+             rowsq_in=rs_in)
     qkv = (normed @ w.double().t() + bias.double()).float().cpu().reshape(m, 3, d // 80, 80)
     c80, s80 = torch.cat([cos, cos], -1).cpu(), torch.cat([sin, sin], -1).cpu()
     q, k = tower_ref.rope_ref(qkv[:, 0], qkv[:, 1], c80, s80)
@@ -195,6 +202,36 @@ def test_gemm_fused_rmsnorm_consumers():
     run_gemm(xb, (w2 * gamma).to(torch.bfloat16), _lib.EPI_SWIGLU, out2, bias=b2, ldo=ipad, rowsq_in=rs_in)
     z = (normed @ w2.double().t() + b2.double()).float()
     close(out2, torch.nn.functional.silu(z[:, 0::2]) * z[:, 1::2], 1e-2)
+
+
+@pytest.mark.parametrize("m,d", [(192, 160), (2048, 1280), (8192 + 64, 320)])
+def test_gemm_qkv_rope_window_attention_fused(m, d):
+    """QKV_ROPE_WINATTN: projection + RoPE + softmax(Q K^T / sqrt(80)) V over windows of 64 consecutive rows, all in
+    the GEMM epilogue, against the unfused restatement (HF :231-261 with cu_window_seqlens = 0, 64, 128, ...)."""
+    nh = d // 80
+    x = rnd((m, d), 30, 2.0, torch.float32)
+    gamma = 1 + 0.1 * rnd((d,), 31, 1.0, torch.float32)
+    w, bias = rnd((3 * d, d), 32, 0.03, torch.float32), rnd((3 * d,), 33, 0.1, torch.float32)   # logits of a few units
+    rope, cos, sin = make_rope(m, 34)
+    xb = x.to(torch.bfloat16)
+    rs_in = rowsq_parts(x).float().to(DEV)
+    out = torch.zeros(m, d, dtype=torch.bfloat16, device=DEV)
+    run_gemm(xb, head_major((w * gamma).to(torch.bfloat16), d), _lib.EPI_QKV_ROPE_WINATTN, out, bias=head_major(bias, d),
+             rope=rope, rowsq_in=rs_in, ldo=d)
+    normed = (x.double() * torch.rsqrt((x.double() ** 2).mean(-1, keepdim=True) + 1e-6)) * gamma.double()
+    qkv = (normed @ w.double().t() + bias.double()).float().cpu().reshape(m, 3, nh, 80)
+    c80, s80 = torch.cat([cos, cos], -1), torch.cat([sin, sin], -1)
+    q, k = tower_ref.rope_ref(qkv[:, 0], qkv[:, 1], c80, s80)
+    v = qkv[:, 2]
+    ref = torch.empty(m, nh, 80)
+    for w0 in range(0, m, 64):
+        qq, kk, vv = (t[w0:w0 + 64].transpose(0, 1) for t in (q, k, v))          # [nh, 64, 80]
+        p = torch.softmax(qq @ kk.transpose(1, 2) / 80 ** 0.5, dim=-1)
+        ref[w0:w0 + 64] = (p @ vv).transpose(0, 1)
+    close(out, ref.reshape(m, d), 1e-2)
+    with pytest.raises(ValueError):                       # windows must tile the rows exactly
+        run_gemm(xb[:100], head_major((w * gamma).to(torch.bfloat16), d), _lib.EPI_QKV_ROPE_WINATTN, out[:100],
+                 bias=head_major(bias, d), rope=rope, ldo=d)
 
 
 def test_pack_weights_c_abi_matches_torch_restatement():
@@ -221,7 +258,9 @@ def test_pack_weights_c_abi_matches_torch_restatement():
 
         g1, g2 = src["blocks.1.norm1.weight"], src["blocks.1.norm2.weight"]
         qkv = dev_tensor(lw.qkv_w, (3 * d, d), torch.bfloat16).cpu()
-        assert torch.equal(qkv, (src["blocks.1.attn.qkv.weight"] * g1).to(torch.bfloat16))
+        assert torch.equal(qkv, head_major((src["blocks.1.attn.qkv.weight"] * g1).to(torch.bfloat16), d))
+        qb = dev_tensor(lw.qkv_b, (3 * d,), torch.float32).cpu()
+        assert torch.equal(qb, head_major(src["blocks.1.attn.qkv.bias"], d))
         gu = dev_tensor(lw.gateup_w, (ipad, 2, d), torch.bfloat16).cpu()
         assert torch.equal(gu[:i, 0], (src["blocks.1.mlp.gate_proj.weight"] * g2).to(torch.bfloat16))
         assert torch.equal(gu[:i, 1], (src["blocks.1.mlp.up_proj.weight"] * g2).to(torch.bfloat16))

@@ -54,7 +54,7 @@ def gemm_fn(m, n, k, epi, ldo=None, rope=False, out_dtype=torch.bfloat16):
     g = _lib.GemmArgs()
     g.d_a, g.d_b, g.d_out, g.d_bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr()
     g.d_rope, g.d_rope_pos = rope_t.data_ptr(), rope_pos.data_ptr()
-    g.m, g.n, g.k, g.ldo, g.rope_cols, g.epilogue = m, n, k, ocols, (2 * n // 3 if rope else 0), epi
+    g.m, g.n, g.k, g.ldo, g.epilogue = m, n, k, ocols, epi
     if epi == _lib.EPI_BIAS_RESIDUAL_NORM or (epi == _lib.EPI_STORE_F32 and fused):
         g.d_out_bf16, g.d_rowsq_out = xb.data_ptr(), rowsq.data_ptr()
         g.d_sync = sync.data_ptr() if os.environ.get("STREAM_K", "1") != "0" else None
