@@ -597,7 +597,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     WorkIter work(num_tiles, num_kb, unit, num_units, (p.stream_k & 1) != 0);
     Segment sg;
 #ifdef B200_GEMM_TIMING
-    long long e_wait = 0, e_busy = 0, e_prev = clock64(), e_start = e_prev, e_lastfull = 0;
+    long long e_wait = 0, e_busy = 0, e_a = 0, e_b = 0, e_c = 0, e_prev = clock64(), e_start = e_prev, e_lastfull = 0;
 #define ESTAMP(v) do { long long _n = clock64(); v += _n - e_prev; e_prev = _n; } while (0)
 #else
 #define ESTAMP(v)
@@ -607,8 +607,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // head-interleaved, so the 240 columns of a tile are Q_h | K_h | V_h of one head h, and a CTA's 128 rows are two
       // 64-patch windows: everything softmax(Q K^T / sqrt(80)) V needs for (2 windows x 1 head) is in this CTA's
       // accumulator.  The 12 epilogue warps stage Q, K (rotated) and V as bf16 in shared memory exactly as the plain
-      // epilogue does -- and then, instead of storing them, eight warps run the attention of 16 query rows each with
-      // warp-level MMAs (5.2 MFLOP per tile against 78.6 MFLOP of projection) and store the 16 x 80 output rows.
+      // epilogue does -- and then, instead of storing them, four warps run the attention of 32 query rows each with
+      // warp-level MMAs (5.2 MFLOP per tile against 78.6 MFLOP of projection) and store the 32 x 80 output rows.
       // Q, K, V never reach L2 / HBM (63 MB written and read back per layer otherwise) and the 28 attention launches
       // disappear.  Overlaps the next tile's main loop like every other epilogue.
       static_assert(CW == 80 && EG == 3, "one head per tile: Q | K | V groups of 80 columns");
@@ -637,88 +637,110 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
           else mbar_arrive(&tempty[as]);
         }
+        ESTAMP(e_a);
         named_barrier(1, EPI_THREADS);  // Q, K, V of the CTA's two windows are staged
-        uint32_t opk[20];               // this warp's 16 x 80 output, bf16 pairs: [dim tile][row half]
-        if (g < 2) {
-          const int w = q >> 1;         // window (rows 64 w .. 64 w + 63 of the CTA) of this warp's 16 query rows
-          const uint32_t qb = stg_all + (0 * 4 + q) * C::STG_WARP + (16 * g) * RS;
+        ESTAMP(e_b);
+        // The GEMM main loop keeps shared memory at its bandwidth limit (TMA writes + operand reads), so the attention
+        // is organised to touch it as little as possible: ONE warp per 32 query rows (the Q warp of each quadrant, on its
+        // own staged rows), so every K / V fragment is read twice per window instead of four times.
+        uint32_t opk[2][20];            // this warp's 32 x 80 output, bf16 pairs: [m tile][dim tile][row half]
+        if (g == 0) {
+          const int w = q >> 1;         // window (rows 64 w .. 64 w + 63 of the CTA) of this warp's 32 query rows
+          const uint32_t qb = stg;      // this warp staged exactly the Q rows it now consumes
           const int lr = (lane & 7) + 8 * ((lane >> 3) & 1), lc = lane >> 4;     // ldmatrix address roles
-          float sacc[8][4];
+          float sacc[2][8][4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sacc[mt][i][0] = sacc[mt][i][1] = sacc[mt][i][2] = sacc[mt][i][3] = 0.f;
 #pragma unroll
           for (int ks = 0; ks < 5; ++ks) {  // S = Q K^T over the 80 head dims, 16 at a time
-            uint32_t a0, a1, a2, a3;
-            ldmatrix_x4(qb + lr * RS + (ks * 16 + 8 * lc) * 2, a0, a1, a2, a3);
+            uint32_t a[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+              ldmatrix_x4(qb + (16 * mt + lr) * RS + (ks * 16 + 8 * lc) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
 #pragma unroll
             for (int nt = 0; nt < 8; nt += 2) {  // keys 8 nt .. 8 nt + 15
               const uint32_t kb = stg_all + (1 * 4 + 2 * w + (nt >> 2)) * C::STG_WARP + ((8 * nt) & 31) * RS;
               uint32_t b0, b1, b2, b3;
               ldmatrix_x4(kb + ((lane & 7) + 8 * lc) * RS + (ks * 16 + 8 * ((lane >> 3) & 1)) * 2, b0, b1, b2, b3);
-              mma_bf16_16816(sacc[nt], a0, a1, a2, a3, b0, b1);
-              mma_bf16_16816(sacc[nt + 1], a0, a1, a2, a3, b2, b3);
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                mma_bf16_16816(sacc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+                mma_bf16_16816(sacc[mt][nt + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b2, b3);
+              }
             }
           }
-          // softmax over the window's 64 keys; a thread holds rows lane/4 and lane/4 + 8, a quad holds a whole row
-          float mx0 = -INFINITY, mx1 = -INFINITY;
+          // softmax over the window's 64 keys; a thread holds rows lane/4 and lane/4 + 8 of each m tile, a quad a whole row
+          uint32_t pa[2][4][4];  // P as A operands of the four 16-key steps
+          float inv[2][2];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            mx0 = fmaxf(mx0, fmaxf(sacc[i][0], sacc[i][1]));
-            mx1 = fmaxf(mx1, fmaxf(sacc[i][2], sacc[i][3]));
+          for (int mt = 0; mt < 2; ++mt) {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              mx0 = fmaxf(mx0, fmaxf(sacc[mt][i][0], sacc[mt][i][1]));
+              mx1 = fmaxf(mx1, fmaxf(sacc[mt][i][2], sacc[mt][i][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float e0 = ex2f((sacc[mt][i][0] - mx0) * scale_log2), e1 = ex2f((sacc[mt][i][1] - mx0) * scale_log2);
+              const float e2 = ex2f((sacc[mt][i][2] - mx1) * scale_log2), e3 = ex2f((sacc[mt][i][3] - mx1) * scale_log2);
+              sum0 += e0 + e1, sum1 += e2 + e3;
+              pa[mt][i >> 1][(i & 1) * 2] = pack_bf16x2(e0, e1);
+              pa[mt][i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(e2, e3);
+            }
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1), sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1), sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+            inv[mt][0] = 1.0f / sum0, inv[mt][1] = 1.0f / sum1;
           }
-          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-          float sum0 = 0.f, sum1 = 0.f;
-          uint32_t pa[4][4];  // P as A operands of the four 16-key steps
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float e0 = ex2f((sacc[i][0] - mx0) * scale_log2), e1 = ex2f((sacc[i][1] - mx0) * scale_log2);
-            const float e2 = ex2f((sacc[i][2] - mx1) * scale_log2), e3 = ex2f((sacc[i][3] - mx1) * scale_log2);
-            sum0 += e0 + e1, sum1 += e2 + e3;
-            pa[i >> 1][(i & 1) * 2] = pack_bf16x2(e0, e1);
-            pa[i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(e2, e3);
-          }
-          sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1), sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-          sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1), sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-          const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+          for (int dp = 0; dp < 5; ++dp) {  // O = P V, two 8-wide dim tiles per pass (register pressure)
+            float oacc[2][2][4];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {  // O = P V, 40 of the 80 dims per pass (register pressure)
-            float oacc[5][4];
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int i = 0; i < 5; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+              for (int i = 0; i < 2; ++i) oacc[mt][i][0] = oacc[mt][i][1] = oacc[mt][i][2] = oacc[mt][i][3] = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {  // keys 16 j .. 16 j + 15
               const uint32_t vb = stg_all + (2 * 4 + 2 * w + (j >> 1)) * C::STG_WARP + ((16 * j) & 31) * RS;
+              uint32_t b0, b1, b2, b3;
+              ldmatrix_x4_trans(vb + lr * RS + (dp * 16 + 8 * lc) * 2, b0, b1, b2, b3);
 #pragma unroll
-              for (int dt = 0; dt < 5; dt += 2) {
-                uint32_t b0, b1, b2, b3;
-                // the fifth dim tile of a pass has no partner: its second half re-reads a valid neighbour and is unused
-                const int d0 = half * 40 + dt * 8, dsec = dt + 1 < 5 ? 8 * lc : 0;
-                ldmatrix_x4_trans(vb + lr * RS + (d0 + dsec) * 2, b0, b1, b2, b3);
-                mma_bf16_16816(oacc[dt], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b0, b1);
-                if (dt + 1 < 5) mma_bf16_16816(oacc[dt + 1], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b2, b3);
+              for (int mt = 0; mt < 2; ++mt) {
+                mma_bf16_16816(oacc[mt][0], pa[mt][j][0], pa[mt][j][1], pa[mt][j][2], pa[mt][j][3], b0, b1);
+                mma_bf16_16816(oacc[mt][1], pa[mt][j][0], pa[mt][j][1], pa[mt][j][2], pa[mt][j][3], b2, b3);
               }
             }
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              opk[(half * 5 + i) * 2] = pack_bf16x2(oacc[i][0] * inv0, oacc[i][1] * inv0);
-              opk[(half * 5 + i) * 2 + 1] = pack_bf16x2(oacc[i][2] * inv1, oacc[i][3] * inv1);
-            }
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                opk[mt][(dp * 2 + i) * 2] = pack_bf16x2(oacc[mt][i][0] * inv[mt][0], oacc[mt][i][1] * inv[mt][0]);
+                opk[mt][(dp * 2 + i) * 2 + 1] = pack_bf16x2(oacc[mt][i][2] * inv[mt][1], oacc[mt][i][3] * inv[mt][1]);
+              }
           }
         }
+        ESTAMP(e_c);
         named_barrier(2, EPI_THREADS);  // every read of the staged Q, K, V is done: the buffers may be reused
-        if (g < 2) {
-          // 16 x 80 bf16, dense 160-byte rows at the start of this warp's own buffer -> one TMA store
+        ESTAMP(e_b);
+        if (g == 0) {
+          // 32 x 80 bf16, dense 160-byte rows at the start of this warp's own buffer -> one TMA store
 #pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            const uint32_t base = stg + (i * 8 + 2 * (lane & 3)) * 2;
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (lane >> 2) * 160), "r"(opk[2 * i]) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + ((lane >> 2) + 8) * 160), "r"(opk[2 * i + 1]) : "memory");
-          }
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+              const uint32_t base = stg + (16 * mt + (lane >> 2)) * 160 + (i * 8 + 2 * (lane & 3)) * 2;
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(base), "r"(opk[mt][2 * i]) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 8 * 160), "r"(opk[mt][2 * i + 1]) : "memory");
+            }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tma_out, stg, head * 80, m0 + q * 32 + 16 * g);
+            tma_store_2d(&tma_out, stg, head * 80, m0 + q * 32);
             bulk_commit();
           }
         }
@@ -889,7 +911,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #ifdef B200_GEMM_TIMING
     if (blockIdx.x == 10 && warp == 4 && lane == 0) {
       const long long tail = clock64() - e_prev;
-      printf("gemm epilogue warp: total %lld | wait tfull %lld | busy %lld | final bulk wait %lld | last tile epilogue %lld\n", clock64() - e_start, e_wait, e_busy, tail, e_lastfull ? clock64() - e_lastfull : 0);
+      printf("gemm epilogue warp: total %lld | wait tfull %lld | busy %lld | final bulk wait %lld | last tile epilogue %lld | fused attention: staging %lld barriers %lld attention %lld\n", clock64() - e_start, e_wait, e_busy, tail, e_lastfull ? clock64() - e_lastfull : 0, e_a, e_b, e_c);
     }
 #endif
   }
@@ -946,7 +968,7 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
     if (is_resid_norm(EPI)) {
       rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, 128);  // reduce-add of stream-K tail partials
     } else if (EPI == B200VIT_EPI_QKV_ROPE_WINATTN) {
-      rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 3, a.ldo, 2, 16, 80, 0);  // attention output [M, D], 16-row boxes
+      rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 3, a.ldo, 2, 32, 80, 0);  // attention output [M, D], 32-row boxes
     } else if (EPI == B200VIT_EPI_QKV_ROPE) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 2, 32, 80, 0);
     else if (EPI == B200VIT_EPI_BIAS_RESIDUAL) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n, a.ldo, 4, 32, 32, 128);
     else if (EPI == B200VIT_EPI_SWIGLU) rc = make_tmap_2d(&g.to, a.d_out, a.m, a.n / 2, a.ldo, 2, 32, 64, 128);

@@ -58,7 +58,7 @@ def gemm_fn(m, n, k, epi, ldo=None, rope=False, out_dtype=torch.bfloat16):
     if epi == _lib.EPI_BIAS_RESIDUAL_NORM or (epi == _lib.EPI_STORE_F32 and fused):
         g.d_out_bf16, g.d_rowsq_out = xb.data_ptr(), rowsq.data_ptr()
         g.d_sync = sync.data_ptr() if os.environ.get("STREAM_K", "1") != "0" else None
-    if epi in (_lib.EPI_QKV_ROPE, _lib.EPI_SWIGLU) and fused:
+    if epi in (_lib.EPI_QKV_ROPE, _lib.EPI_SWIGLU, _lib.EPI_QKV_ROPE_WINATTN) and fused:
         g.d_rowsq_in, g.rowsq_parts, g.norm_eps = rowsq.data_ptr(), 10, 1e-6
     keep = (a, b, bias, out, rope_t, rope_pos, xb, rowsq, sync)
 
@@ -74,6 +74,7 @@ def main():
     shapes = [
         ("patch_embed", M, D, 1176, _lib.EPI_STORE_F32, None, False, torch.float32),
         ("qkv_rope", M, 3 * D, D, _lib.EPI_QKV_ROPE, None, True, torch.bfloat16),
+        ("qkv_rope_winattn", M, 3 * D, D, _lib.EPI_QKV_ROPE_WINATTN, D, True, torch.bfloat16),
         ("proj_resid", M, D, D, _lib.EPI_BIAS_RESIDUAL_NORM, None, False, torch.float32),
         ("proj_old", M, D, D, _lib.EPI_BIAS_RESIDUAL, None, False, torch.float32),
         ("gateup_swiglu", M, 2 * IPAD, D, _lib.EPI_SWIGLU, IPAD, False, torch.bfloat16),

@@ -12,6 +12,7 @@ M, D, IPAD = bench_ops.M, 1280, 3456
 SHAPES = {
     "patch_embed": (M, D, 1176, _lib.EPI_STORE_F32, None, False, torch.float32),
     "qkv": (M, 3 * D, D, _lib.EPI_QKV_ROPE, None, True, torch.bfloat16),
+    "qkvwin": (M, 3 * D, D, _lib.EPI_QKV_ROPE_WINATTN, D, True, torch.bfloat16),
     "proj": (M, D, D, _lib.EPI_BIAS_RESIDUAL_NORM, None, False, torch.float32),
     "gateup": (M, 2 * IPAD, D, _lib.EPI_SWIGLU, IPAD, False, torch.bfloat16),
     "down": (M, D, IPAD, _lib.EPI_BIAS_RESIDUAL_NORM, None, False, torch.float32),
