@@ -6,10 +6,12 @@ TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 KREGEX='regex:gemm_tcgen05|attn_tc|attn_full2|rmsnorm_kernel|overlay_patchify|cast_bf16|raster_kernel'
+if [ -z "$ONLY_CAPS" ]; then
 # ---- launch list: skip the warm-up forwards (138 launches each incl. none from torch), take two forwards
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 552 -c 276 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline > $OUT/${TAG}_launches_bench.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < $OUT/${TAG}_launches.csv)"
+fi
 METRICS='gpu__time_duration.sum|dram__bytes_read.sum |dram__bytes_write.sum |dram__bytes_read.sum,|dram__bytes_write.sum,|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|sm__pipe_tensor_cycles_active|sm__inst_executed_pipe_tensor|sm__warps_active.avg.pct_of_peak_sustained_active|launch__registers_per_thread|launch__grid_size|launch__block_size|sm__throughput.avg.pct|lts__t_bytes.sum |lts__t_bytes.sum,|l1tex__data_pipe_lsu_wavefronts_mem_shared.sum |l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,|smsp__cycles_active.avg|sm__cycles_elapsed.max|smsp__inst_executed.sum |smsp__inst_executed.sum,|lts__t_sector_hit_rate.pct|sm__pipe_tensor_op_hmma|smsp__issue_active.avg.pct'
 cap() {   # name, kernel regex, skip, command...
   local name=$1 kre=$2 skip=$3; shift 3
@@ -31,11 +33,13 @@ with open(sys.argv[2], "w") as f:
 print("  ->", sys.argv[2])
 PY
 }
-cap gateup 'gemm_tcgen05_kernel<256, 2, 3' 8 python tools/prof_gemm.py gateup 2
-cap qkv_winattn 'gemm_tcgen05_kernel<240, 3, 8' 8 python tools/prof_gemm.py qkvwin 2
-cap qkv 'gemm_tcgen05_kernel<240, 3, 1' 8 python tools/prof_gemm.py qkv 2
-cap proj 'gemm_tcgen05_kernel<256, 2, 7' 8 python tools/prof_gemm.py proj 2
-cap down 'gemm_tcgen05_kernel<256, 2, 7' 8 python tools/prof_gemm.py down 2
+cap gateup 'gemm_tcgen05' 8 python tools/prof_gemm.py gateup 2
+cap qkv_winattn 'gemm_tcgen05' 8 python tools/prof_gemm.py qkvwin 2
+cap qkv 'gemm_tcgen05' 8 python tools/prof_gemm.py qkv 2
+cap proj 'gemm_tcgen05' 8 python tools/prof_gemm.py proj 2
+cap down 'gemm_tcgen05' 8 python tools/prof_gemm.py down 2
+if [ -z "$ONLY_CAPS" ]; then
 cap attn_full 'attn_full2' 4 python tools/prof_attn.py 1024 2
 cap overlay 'overlay_patchify' 6 python tools/prof_overlay.py
+fi
 ls -la $OUT | grep ${TAG}_ | head -40
