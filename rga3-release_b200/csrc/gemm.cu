@@ -90,7 +90,7 @@ __host__ __device__ constexpr int epi_stage_bytes(int epi) {
          : is_resid_norm(epi) ? 4096  // one 32 x 32 fp32 chunk of (acc + bias) in transit between the two thread layouts
          : epi == B200VIT_EPI_SWIGLU        ? 4096
          : epi == B200VIT_EPI_BIAS_GELU     ? 2 * 4096
-                                            : 0;
+                                            : 4096;  // row-mapped epilogues: one chunk in transit between thread layouts
 }
 
 // PAIR = true: two CTAs of a cluster cooperate on a 256 x BN tile with tcgen05.mma.cta_group::2 --
@@ -292,55 +292,64 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
       }
     }
   } else {
-    // row-mapped outputs (window reorder of the patch embed, un-reorder of the merger): direct stores
+    // Row-mapped outputs (window reorder of the patch embed, un-reorder of the merger).  A thread owns one accumulator
+    // ROW, but a warp store should cover whole 128-byte lines: every 32 x 32 chunk is transposed through 4 KB of
+    // swizzled shared memory (written row-per-thread, read back 8 lanes per row), then each row's 128 bytes leave in
+    // one piece to wherever row_map sends that row.  STORE_F32 also emits the bf16 copy and the row's sum of squares
+    // (the first fused RMSNorm's inputs).
     static_assert(CW % 32 == 0, "generic epilogues work in 32-column chunks");
-    const int orow = (row_ok && p.row_map != nullptr) ? p.row_map[row] : row;
-    float ss = 0.f;  // STORE_F32: sum of squares of this thread's CW columns (partial of the next RMSNorm)
+    const int lr = lane >> 3, lc = (lane & 7) * 4;  // coalesced layout: row 4 i + lr (i = 0..7), columns lc .. lc + 3
+    int orow[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = row0 + 4 * i + lr;
+      orow[i] = r < p.m ? (p.row_map != nullptr ? __ldg(p.row_map + r) : r) : -1;
+    }
+    float ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss[i] = 0.f;
 #pragma unroll 1
     for (int c = 0; c < CW; c += 32) {
       uint32_t v[32];
       tmem_ld32(taddr + c, v);
-      const int col = col0 + c;
+      const int col = col0 + c + lc;
+      const bool col_ok = col + 4 <= p.n;
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (EPI != B200VIT_EPI_STORE_F32) bb = bias4(p.bias, col, p.n);
       tmem_ld_wait();
-      if (!row_ok) continue;
-      if constexpr (EPI == B200VIT_EPI_STORE_F32 || EPI == B200VIT_EPI_BIAS_F32) {
-        float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo + col;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (col + 4 * j + 4 <= p.n) {
-            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            if constexpr (EPI == B200VIT_EPI_BIAS_F32) {
-              const float4 b = ldg4(p.bias + col + 4 * j);
-              o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
-            }
-            *reinterpret_cast<float4*>(op + 4 * j) = o;
-            if constexpr (EPI == B200VIT_EPI_STORE_F32) {
-              ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-              if (p.out_bf16 != nullptr)
-                *reinterpret_cast<uint2*>(p.out_bf16 + static_cast<size_t>(orow) * p.ldo + col + 4 * j) =
-                    make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-            }
-          }
-        }
-      } else {  // BIAS_BF16
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(orow) * p.ldo + col;
+      for (int j = 0; j < 8; ++j) st_shared_v4(swz128(stg, lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          if (col + 8 * h + 8 <= p.n) {
-            const float4 b0 = ldg4(p.bias + col + 8 * h), b1 = ldg4(p.bias + col + 8 * h + 4);
-            *reinterpret_cast<uint4*>(op + 8 * h) =
-                make_uint4(pack_bf16x2(__uint_as_float(v[8 * h]) + b0.x, __uint_as_float(v[8 * h + 1]) + b0.y),
-                           pack_bf16x2(__uint_as_float(v[8 * h + 2]) + b0.z, __uint_as_float(v[8 * h + 3]) + b0.w),
-                           pack_bf16x2(__uint_as_float(v[8 * h + 4]) + b1.x, __uint_as_float(v[8 * h + 5]) + b1.y),
-                           pack_bf16x2(__uint_as_float(v[8 * h + 6]) + b1.z, __uint_as_float(v[8 * h + 7]) + b1.w));
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = ld_shared_f4(swz128(stg, 4 * i + lr, lane & 7));
+        const float4 o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+        if (orow[i] < 0 || !col_ok) continue;
+        const size_t off = static_cast<size_t>(orow[i]) * p.ldo + col;
+        if constexpr (EPI == B200VIT_EPI_BIAS_BF16) {
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = o;
+          if constexpr (EPI == B200VIT_EPI_STORE_F32) {
+            ss[i] += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+            if (p.out_bf16 != nullptr)
+              *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
           }
         }
       }
+      __syncwarp();  // every lane has read the chunk back before the next one overwrites it
     }
     if constexpr (EPI == B200VIT_EPI_STORE_F32) {
-      if (row_ok && p.rowsq_out != nullptr && col0 < p.n)
-        p.rowsq_out[static_cast<size_t>(col0 / CW) * p.m + orow] = ss;
+      // row sums: the 8 lanes that share a row combine their column partials in a fixed tree
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s8 = ss[i];
+        s8 += __shfl_xor_sync(0xffffffffu, s8, 1);
+        s8 += __shfl_xor_sync(0xffffffffu, s8, 2);
+        s8 += __shfl_xor_sync(0xffffffffu, s8, 4);
+        if ((lane & 7) == 0 && p.rowsq_out != nullptr && orow[i] >= 0 && col0 < p.n)
+          p.rowsq_out[static_cast<size_t>(col0 / CW) * p.m + orow[i]] = s8;
+      }
     }
   }
 }
