@@ -356,10 +356,11 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row0, int lane
 
 // ------------------------------------------------------------------ work decomposition
 // A "segment" is a contiguous range of k-blocks of one output tile.  Data-parallel mode: unit u
-// takes whole tiles u, u + U, ...  Stream-K mode (reduce-add epilogues only): the flattened
+// takes whole tiles u, u + U, ...  Stream-K mode (BIAS_RESIDUAL_NORM only): the flattened
 // (tile, k-block) space is cut into U equal ranges, so all CTA pairs finish together even when
 // the tile count is a poor multiple of the pair count (N = 1280 at M = 8192: 160 tiles on 74
-// pairs); tiles cut by a range boundary are completed by several partial reduce-adds.
+// pairs); a tile cut by a range boundary is finished by exactly two units in a fixed order (tail
+// partial reduce-added first, then the head unit's epilogue; see the epilogue for the hand-over).
 struct Segment {
   int tile, kb0, kb1;
 };
@@ -465,12 +466,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   }
   tc_fence_before();
-  if constexpr (PAIR) {
-    cluster_sync_all();
-    __syncthreads();  // redundant after the cluster barrier; lets compute-sanitizer racecheck see the ordering of tmem_slot
-  } else {
-    __syncthreads();
-  }
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  Each role executes
