@@ -800,6 +800,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           ld_x(xr, row0, col0);  // in flight while the tile's main loop finishes
         }
+        float4 bb = bias4(p.bias, col0 + lc, p.n);  // likewise: an L2 round trip per chunk otherwise (ncu: top stall)
         ESTAMP(e_busy);
         mbar_wait(&tfull[as], aph);
         tc_fence_after();
@@ -837,8 +838,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             tmem_ld32(taddr + c, v);
             const int col = col0 + c;
             float4 xn[8];
-            if (c + 32 < CW) ld_x(xn, row0, col + 32);  // next chunk's old x
-            const float4 bb = bias4(p.bias, col + lc, p.n);
+            float4 bn = bb;
+            if (c + 32 < CW) {
+              ld_x(xn, row0, col + 32);  // next chunk's old x and bias
+              bn = bias4(p.bias, col + 32 + lc, p.n);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) st_shared_v4(swz128(xs, lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -861,6 +865,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             if (c + 32 < CW) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) xr[i] = xn[i];
+              bb = bn;
             }
           }
           // row sums: the 8 lanes that share a row combine their column partials in a fixed tree
