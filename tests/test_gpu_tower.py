@@ -33,7 +33,8 @@ def make_tower(cfg_kwargs, seed=0, **kw):
     return t, cfg, sd
 
 
-@pytest.mark.parametrize("grid", [[[2, 8, 12]], [[1, 6, 10], [2, 4, 8]], [[1, 2, 2]], [[3, 18, 14]]])
+@pytest.mark.parametrize("grid", [[[2, 8, 12]], [[1, 6, 10], [2, 4, 8]], [[1, 2, 2]], [[3, 18, 14]],
+                                  [[2, 8, 8]], [[1, 16, 8], [2, 8, 16]]])   # the last two: every window 64 rows -> fused attention path
 def test_tower_tiny_vs_oracle(grid):
     t, cfg, sd = make_tower(hf_ref.CFG_TINY, output_fp32=True)
     m = sum(a * b * c for a, b, c in grid)
