@@ -538,9 +538,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 // softmax is issue/latency-bound with one thread per row (phase timings: 3.1 k cycles per block and tile), so every row is
 // split between TWO threads (64 score columns / 40 output columns each; 16 softmax warps instead of 8).  The partners
 // exchange their partial row maximum through shared memory once per block and their partial row sums once at the end.
-constexpr int F2_THREADS = 64 + 512;
-
-__global__ void __launch_bounds__(F2_THREADS, 1)
+//
+// O stays in TMEM for the whole K/V walk: P.V(j) accumulates onto P.V(j-1) and the softmax warps never read a per-block
+// O back.  The running maximum is therefore LAZY: a row keeps the maximum m it used so far while the new block's maximum
+// stays below m + 8 (log2 units; P <= 2^8, harmless in bf16 / fp32), and only when it grows past that do the row's two
+// threads rescale their 40 O columns in TMEM (tcgen05.ld -> *2^(m - m') -> tcgen05.st) and their partial sums.  After the
+// first block that is rare, so the per-block chain of a tile is  S wait -> row max -> exp2 pass -> P.V  instead of
+// ... -> O drain (80 FFMA per row) -> P.V, and the O hand-shake (o_empty) is gone.
+constexpr float RESCALE_LOG2 = 8.f;
+#ifndef B200_ATTN_DBG
+#define B200_ATTN_DBG 0
+#endif
+// TPR = threads per query row (2: as described above; 1: one thread owns the whole row -- 8 softmax warps, no partner
+// exchange, 128 score registers).
+template <int TPR>
+__global__ void __launch_bounds__(96 + 256 * TPR, 1)
 attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                   const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap to16,
                   const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, int m_rows, int heads,
@@ -559,8 +571,8 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
   uint64_t* s_full = v_empty + NKV;  // [2]
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = p_full + 2;
-  uint64_t* o_empty = o_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* s_free = o_full + 2;  // [2] softmax(t, j) holds S(t) in registers: Q.K^T(j+1) may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
   float* exch = reinterpret_cast<float*>(smem + L::OFF_BAR + 256);  // [2 parities][2 tiles][2 halves][128] floats = 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -577,15 +589,15 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
     mbar_init(q_full, 1);
     for (int b = 0; b < NKV; ++b) {
       mbar_init(&k_full[b], 1);
-      mbar_init(&k_empty[b], 1);
+      mbar_init(&k_empty[b], 2);  // one commit per tile's issuing warp
       mbar_init(&v_full[b], 1);
-      mbar_init(&v_empty[b], 1);
+      mbar_init(&v_empty[b], 2);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 256);
+      mbar_init(&p_full[t], 128 * TPR);
       mbar_init(&o_full[t], 1);
-      mbar_init(&o_empty[t], 256);
+      mbar_init(&s_free[t], 128 * TPR);
     }
     fence_barrier_init();
   }
@@ -623,7 +635,7 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
         load_v(smem + L::OFF_V + b * V_TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= 2) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = idesc_bf16(QT, KVB, false);
       constexpr uint32_t idesc_pv = idesc_bf16(QT, HD, true);
@@ -637,222 +649,147 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
         umma_bf16_ss(ts, desc_k_sw32(q16), desc_k_sw32(k16), idesc_qk, 1u);
         umma_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int i) {
+      auto issue_pv = [&](int t, int i) {  // O(t) += P(t) V(i): the softmax warps rescale O themselves when a row maximum grows
         mbar_wait(&p_full[t], i & 1);
-        mbar_wait(&o_empty[t], (i & 1) ^ 1);
         tc_fence_after();
         const uint32_t p0 = smem_u32(smem + L::OFF_P + t * P_BYTES);
         const uint32_t v64 = smem_u32(smem + L::OFF_V + (i % NKV) * V_TILE_BYTES);
         const uint32_t to = tmem_base + L::O_COL(t);
+#if B200_ATTN_DBG == 2
+        if (i == 0)
+#endif
 #pragma unroll
         for (int k = 0; k < KVB / 16; ++k) {
           const uint64_t pa = umma_desc_k128(p0 + (k >> 2) * T64_BYTES + (k & 3) * 32);
-          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv, k != 0 ? 1u : 0u);
+          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv, (i != 0 || k != 0) ? 1u : 0u);
         }
         umma_commit(&o_full[t]);
       };
-#ifdef B200_ATTN_TIMING
-      long long mt[4] = {0, 0, 0, 0};
-      long long mprev = clock64();
-#define MSTAMP(k) do { long long _n = clock64(); mt[k] += _n - mprev; mprev = _n; } while (0)
-#else
-#define MSTAMP(k)
-#endif
+      // One issuing warp per query tile, each walking its own tile's fixed order
+      //     Q.K^T(0);  for i: [S(t) read by softmax(i): Q.K^T(i+1)]  [P(t, i) written: P.V(i)]
+      // on blocking (hardware-suspended) mbarrier waits: the softmax warps release S(t) as soon as a block's scores are
+      // in their registers, so Q.K^T(i+1) runs underneath softmax(i) and S(i+1) is waiting when they come back.  (A single
+      // issuer polling both tiles with nanosleep between probes reacted a block period late: the sleep quantum is ~1 us.)
+      // The tensor pipe interleaves the two tiles' MMAs in arrival order; a K/V stage is released when BOTH tiles' warps
+      // have committed their use of it (k_empty / v_empty count 2).
+      const int t = warp - 1;
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      MSTAMP(0);
-      for (int t = 0; t < 2; ++t) issue_qk(t, 0);
+      issue_qk(t, 0);
       umma_commit(&k_empty[0]);
-#ifdef B200_ATTN_MMA_SERIAL
-      // measurement only: run every MMA group to completion before issuing the next one and time it
       for (int i = 0; i < nblk; ++i) {
-        const int b = i % NKV;
-        mbar_wait(&v_full[b], (i / NKV) & 1);
-        const bool more = i + 1 < nblk;
-        if (more) mbar_wait(&k_full[(i + 1) % NKV], ((i + 1) / NKV) & 1);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], i & 1);
-          mbar_wait(&o_empty[t], (i & 1) ^ 1);
-          long long c0 = clock64();
-          issue_pv(t, i);
-          mbar_wait(&o_full[t], i & 1);
-          long long c1 = clock64();
-          if (more) {
-            issue_qk(t, i + 1);
-            mbar_wait(&s_full[t], (i + 1) & 1);
-          }
-          long long c2 = clock64();
-          mt[3] += c1 - c0;
-          if (more) mt[2] += c2 - c1;
+        if (i + 1 < nblk) {
+          mbar_wait(&s_free[t], i & 1);
+          mbar_wait(&k_full[(i + 1) % NKV], ((i + 1) / NKV) & 1);
+          tc_fence_after();
+          issue_qk(t, i + 1);
+          umma_commit(&k_empty[(i + 1) % NKV]);
         }
-        umma_commit(&v_empty[b]);
-        if (more) umma_commit(&k_empty[(i + 1) % NKV]);
+        mbar_wait(&v_full[i % NKV], (i / NKV) & 1);
+        issue_pv(t, i);  // waits for p_full(t, i)
+        umma_commit(&v_empty[i % NKV]);
       }
-      if (blockIdx.x == 1 && blockIdx.y == 0) printf("full2 serial mma: pv total %lld (%d groups) | qk total %lld (%d groups)\n", mt[3], 2 * nblk, mt[2], 2 * (nblk - 1));
-#else
-      // The two tiles advance independently (whichever tile's softmax has delivered P is served, so one tile's softmax
-      // overlaps the other tile's tensor-core work), and inside a tile the NEXT Q.K^T goes ahead of the current P.V:
-      // S(t) is free as soon as softmax(i) has read it, so S(i+1) is produced while the softmax warps still fold
-      // O(i-1) into their registers; P.V(i) follows when they have drained O(t).  The softmax warps wait for P.V(i)
-      // before they overwrite P (see below).  A K/V stage is released by the LATER of the two tiles.
-      int qk_done[2] = {1, 1}, pv_done[2] = {0, 0};
-      const long long t_start = clock64();
-      while (pv_done[0] < nblk || pv_done[1] < nblk) {
-        bool progressed = false;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          int i = qk_done[t];
-          if (i < nblk && mbar_test(&p_full[t], (i - 1) & 1) && mbar_test(&k_full[i % NKV], (i / NKV) & 1)) {
-            tc_fence_after();
-            issue_qk(t, i);
-            qk_done[t] = i + 1;
-            if (qk_done[t ^ 1] > i) umma_commit(&k_empty[i % NKV]);
-            progressed = true;
-          }
-          i = pv_done[t];
-          if (i < nblk && (qk_done[t] > i + 1 || i + 1 >= nblk) && mbar_test(&p_full[t], i & 1) &&
-              mbar_test(&o_empty[t], (i & 1) ^ 1) && mbar_test(&v_full[i % NKV], (i / NKV) & 1)) {
-            issue_pv(t, i);  // its own waits succeed immediately
-            pv_done[t] = i + 1;
-            if (pv_done[t ^ 1] > i) umma_commit(&v_empty[i % NKV]);
-            progressed = true;
-          }
-        }
-        if (!progressed) {
-          __nanosleep(40);
-          if (clock64() - t_start > 8000000000ll) {
-            printf("b200vit: attention scheduler timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
-            __trap();
-          }
-        }
-      }
-#endif
-#ifdef B200_ATTN_TIMING
-      MSTAMP(1);
-      if (blockIdx.x == 1 && blockIdx.y == 0) printf("full2 mma thread: first loads %lld | scheduling loop %lld\n", mt[0], mt[1]);
-#endif
     }
   } else {
     // ===================== softmax + accumulation: two threads per query row =====================
-    const int sw = warp - 2;
-    const int t = sw >> 3;          // query tile
-    const int half = (sw >> 2) & 1; // score columns [64*half, +64), output columns [40*half, +40)
+    constexpr int SC = 128 / TPR;  // score columns per thread
+    constexpr int OC = HD / TPR;   // output columns per thread
+    const int sw = warp - 3;
+    const int t = sw / (4 * TPR);               // query tile
+    const int half = TPR == 2 ? (sw >> 2) & 1 : 0;  // score columns [SC*half, +SC), output columns [OC*half, +OC)
     const int quad = warp & 3;      // TMEM lane quadrant
     const int r = quad * 32 + lane;
     const int row = tile.q_row0 + t * QT + r;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t ts = lane_base + L::S_COL(t) + half * 64;
-    const uint32_t to = lane_base + L::O_COL(t) + half * 40;
-    const uint32_t psub = smem_u32(smem + L::OFF_P + t * P_BYTES) + half * T64_BYTES;  // this half's 64-wide P sub-tile
-    const int bar_id = 1 + t;
+    const uint32_t ts = lane_base + L::S_COL(t) + half * SC;
+    const uint32_t to = lane_base + L::O_COL(t) + half * OC;
+    const uint32_t psub = smem_u32(smem + L::OFF_P + t * P_BYTES) + half * T64_BYTES;  // this thread's first 64-wide P sub-tile
+    const int pair_bar = 3 + t * 4 + quad;  // the two warps that share this tile's rows [32 quad, +32): partner exchange
     int2 bd = make_int2(0, 0);
     if (row < m_rows) bd = bounds[row];
-    float o[40];
-#pragma unroll
-    for (int i = 0; i < 40; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_part = 0.f, alpha_prev = 1.f;
+    float m_used = -INFINITY, l_part = 0.f;  // the maximum the row's probabilities are currently expressed against
 #ifdef B200_ATTN_TIMING
     long long tstamp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
-    const bool trec = (blockIdx.x == 1 && blockIdx.y == 0 && (warp == 2 || warp == 14) && lane == 0);
+    const bool trec = (blockIdx.x == 1 && blockIdx.y == 0 && (warp == 3 || warp == 3 + 4 * TPR) && lane == 0);
+    int n_rescale = 0;
 #define TSTAMP2(k) do { long long _n = clock64(); tstamp[k] += _n - tprev; tprev = _n; } while (0)
 #else
 #define TSTAMP2(k)
 #endif
-
-    auto accumulate_block = [&](int i, float alpha) {
-      mbar_wait(&o_full[t], i & 1);
-      tc_fence_after();
-      uint32_t v[32], v8[8];
-      tmem_ld32(to, v);
-      tmem_ld8(to + 32, v8);
-      tmem_ld_wait();
-      const uint64_t al2 = f32x2_pack(alpha, alpha);
-#pragma unroll
-      for (int i2 = 0; i2 < 32; i2 += 2)
-        f32x2_unpack(f32x2_fma(f32x2_pack(o[i2], o[i2 + 1]), al2, f32x2_pack_bits(v[i2], v[i2 + 1])), o[i2], o[i2 + 1]);
-#pragma unroll
-      for (int i2 = 0; i2 < 8; i2 += 2)
-        f32x2_unpack(f32x2_fma(f32x2_pack(o[32 + i2], o[33 + i2]), al2, f32x2_pack_bits(v8[i2], v8[i2 + 1])), o[32 + i2],
-                     o[33 + i2]);
-      tc_fence_before();
-      mbar_arrive(&o_empty[t]);
-    };
 
     for (int j = 0; j < nblk; ++j) {
       TSTAMP2(0);
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       TSTAMP2(1);
-      const int kv0 = tile.kv_row0 + j * KVB + half * 64;            // first kv row of this thread's column half
-      const int lo = max(bd.x - kv0, 0), hi = min(bd.y - kv0, 64);   // valid columns inside the half
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        if (__all_sync(0xffffffffu, c + 32 <= lo || c >= hi)) continue;
-        uint32_t v[32];
-        TSTAMP2(2);
-        tmem_ld32(ts + c, v);
-        tmem_ld_wait();
-        TSTAMP2(9);
-        if (__all_sync(0xffffffffu, c >= lo && c + 32 <= hi)) {
-          float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
+      const int kv0 = tile.kv_row0 + j * KVB + half * SC;            // first kv row of this thread's columns
+      const int lo = max(bd.x - kv0, 0), hi = min(bd.y - kv0, SC);   // valid columns among them
+      // this thread's share of the S(t) row into registers, then S(t) is free for Q.K^T(j+1)
+      uint32_t sv[SC];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m4[0] = fmaxf(m4[0], __uint_as_float(v[i]));
-            m4[1] = fmaxf(m4[1], __uint_as_float(v[i + 1]));
-            m4[2] = fmaxf(m4[2], __uint_as_float(v[i + 2]));
-            m4[3] = fmaxf(m4[3], __uint_as_float(v[i + 3]));
-          }
-          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        } else {
+      for (int c = 0; c < SC; c += 32) tmem_ld32(ts + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);
+      const bool all_valid = __all_sync(0xffffffffu, lo == 0 && hi == SC);
+      float mx;
+      if (all_valid) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (fmax3 pairs them up)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i >= lo && c + i < hi) ? __uint_as_float(v[i]) : -INFINITY);
+        for (int i = 0; i < SC; i += 4) {
+          m4[0] = fmaxf(m4[0], __uint_as_float(sv[i]));
+          m4[1] = fmaxf(m4[1], __uint_as_float(sv[i + 1]));
+          m4[2] = fmaxf(m4[2], __uint_as_float(sv[i + 2]));
+          m4[3] = fmaxf(m4[3], __uint_as_float(sv[i + 3]));
         }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+        mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < SC; ++i) mx = fmaxf(mx, (i >= lo && i < hi) ? __uint_as_float(sv[i]) : -INFINITY);
       }
-      // partner exchange of the partial row maximum (double-buffered by block parity)
-      float* ex = exch + ((j & 1) * 2 + t) * 256;
       TSTAMP2(2);
-      ex[half * 128 + r] = mx;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, ex[(half ^ 1) * 128 + r]);
+      if constexpr (TPR == 2) {  // partner exchange of the partial row maximum (double-buffered by block parity)
+        float* ex = exch + ((j & 1) * 2 + t) * 256;
+        ex[half * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, ex[(half ^ 1) * 128 + r]);
+      }
       TSTAMP2(3);
-      const float m_new = fmaxf(m_run, mx * scale_log2);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2_approx(m_run - m_use);
+      // lazy maximum: both partners see the same mx, so they take the same decision
+      const float m_blk = mx * scale_log2;
+      const bool grow = m_blk > m_used + RESCALE_LOG2;  // also the first block with a valid column (m_used = -inf)
+      float alpha = 1.f;
+      if (grow) {
+        alpha = ex2_approx(m_used - m_blk);  // m_used = -inf -> 0
+        m_used = m_blk;
+      }
+      const float m_use = (m_used == -INFINITY) ? 0.f : m_used;  // nothing valid so far: p = 0, no NaN
+      l_part *= alpha;
       float sum = 0.f;
-      if (j >= 1) mbar_wait(&o_full[t], (j - 1) & 1);  // P.V(j-1) has finished reading P before it is overwritten
-      TSTAMP2(7);
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        const int j0 = c >> 3;
-        if (__all_sync(0xffffffffu, c + 32 <= lo || c >= hi)) {
+      uint32_t pk[SC / 2];  // this thread's probabilities, bf16
 #pragma unroll
-          for (int q = 0; q < 4; ++q) st_shared_v4(swz128(psub, r, j0 + q), 0u, 0u, 0u, 0u);
-          continue;
-        }
-        uint32_t v[32];
-        TSTAMP2(4);
-        tmem_ld32(ts + c, v);
-        tmem_ld_wait();
-        TSTAMP2(8);
-        uint32_t pk[16];
-        if (__all_sync(0xffffffffu, c >= lo && c + 32 <= hi)) {
-          // packed fp32x2 FFMA / FADD: the softmax is issue-bound (ncu: 0.48 IPC with 3.4 k instructions per block and
-          // sub-partition), so two lanes per issue slot for everything except the MUFU itself
+      for (int c = 0; c < SC; c += 32) {
+        if (all_valid) {
+          // packed fp32x2 FFMA / FADD: two lanes per issue slot for everything except the MUFU itself
           const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), nm2 = f32x2_pack(-m_use, -m_use);
           uint64_t s2a = 0ull, s2b = 0ull;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float x0, x1, x2, x3;
-            f32x2_unpack(f32x2_fma(f32x2_pack_bits(v[i], v[i + 1]), sc2, nm2), x0, x1);
-            f32x2_unpack(f32x2_fma(f32x2_pack_bits(v[i + 2], v[i + 3]), sc2, nm2), x2, x3);
+            f32x2_unpack(f32x2_fma(f32x2_pack_bits(sv[c + i], sv[c + i + 1]), sc2, nm2), x0, x1);
+            f32x2_unpack(f32x2_fma(f32x2_pack_bits(sv[c + i + 2], sv[c + i + 3]), sc2, nm2), x2, x3);
+#if B200_ATTN_DBG == 1
+            const float p0 = x0 * 0.001f, p1 = x1 * 0.001f, p2 = x2 * 0.001f, p3 = x3 * 0.001f;
+#else
             const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+#endif
             s2a = f32x2_add(s2a, f32x2_pack(p0, p1));
             s2b = f32x2_add(s2b, f32x2_pack(p2, p3));
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
+            pk[((c + i) >> 1) + 1] = pack_bf16x2(p2, p3);
           }
           float sa, sb, sc, sd;
           f32x2_unpack(s2a, sa, sb);
@@ -861,51 +798,92 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(__uint_as_float(v[i]) * scale_log2 - m_use);
-            float p1 = ex2_approx(__uint_as_float(v[i + 1]) * scale_log2 - m_use);
+            float p0 = ex2_approx(__uint_as_float(sv[c + i]) * scale_log2 - m_use);
+            float p1 = ex2_approx(__uint_as_float(sv[c + i + 1]) * scale_log2 - m_use);
             p0 = (c + i >= lo && c + i < hi) ? p0 : 0.f;
             p1 = (c + i + 1 >= lo && c + i + 1 < hi) ? p1 : 0.f;
             sum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
           }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          st_shared_v4(swz128(psub, r, j0 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
-      l_part = l_part * alpha + sum;
-      m_run = m_new;
+      if (j >= 1) {
+        // every probability of the block is computed: only now is P.V(j-1) needed (P may be overwritten, O is at rest)
+        TSTAMP2(4);
+        mbar_wait(&o_full[t], (j - 1) & 1);
+        TSTAMP2(7);
+        if (__any_sync(0xffffffffu, grow)) {  // rare after the first block: O(row) *= 2^(m_old - m_new) in TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < OC; c0 += 40) {  // 40 columns (32 + 8) per trip
+            uint32_t v[32], v8[8];
+            tmem_ld32(to + c0, v);
+            tmem_ld8(to + c0 + 32, v8);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v8[i] = __float_as_uint(__uint_as_float(v8[i]) * alpha);
+            tmem_st32(to + c0, v);
+            tmem_st8(to + c0 + 32, v8);
+          }
+          tmem_st_wait();
+#ifdef B200_ATTN_TIMING
+          ++n_rescale;
+#endif
+        }
+        TSTAMP2(6);
+      }
+#pragma unroll
+      for (int q = 0; q < SC / 8; ++q)  // 16-byte chunk q of this thread's columns: sub-tile q / 8, chunk q % 8
+        st_shared_v4(swz128(psub + (q >> 3) * T64_BYTES, r, q & 7), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      l_part += sum;
       TSTAMP2(4);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
       TSTAMP2(5);
-      if (j >= 1) accumulate_block(j - 1, alpha_prev);
-      TSTAMP2(6);
-      alpha_prev = alpha;
     }
-    accumulate_block(nblk - 1, alpha_prev);
-    TSTAMP2(6);
+    // the finished O of this thread's 40 columns
+    mbar_wait(&o_full[t], (nblk - 1) & 1);
+    tc_fence_after();
+    float o[OC];
+#pragma unroll
+    for (int c0 = 0; c0 < OC; c0 += 40) {
+      uint32_t v[32], v8[8];
+      tmem_ld32(to + c0, v);
+      tmem_ld8(to + c0 + 32, v8);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c0 + i] = __uint_as_float(v[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[c0 + 32 + i] = __uint_as_float(v8[i]);
+    }
+    TSTAMP2(8);
 
     // combine the partners' partial row sums, then stage O (bf16) in this warp's own rows of the idle P buffer
-    float* ex = exch + ((nblk & 1) * 2 + t) * 256;
-    ex[half * 128 + r] = l_part;
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-    const float l = l_part + ex[(half ^ 1) * 128 + r];
+    float l = l_part;
+    if constexpr (TPR == 2) {
+      float* ex = exch + ((nblk & 1) * 2 + t) * 256;
+      ex[half * 128 + r] = l_part;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l += ex[(half ^ 1) * 128 + r];
+    }
     const float inv = (l > 0.f) ? 1.f / l : 0.f;
     const uint32_t pbuf = smem_u32(smem + L::OFF_P + t * P_BYTES);
     const uint32_t stg64 = pbuf + quad * 4096;              // [32 rows x 64 cols], SWIZZLE_128B
     const uint32_t stg16 = pbuf + T64_BYTES + quad * 4096;  // [32 rows x 16 cols], dense
 #pragma unroll
-    for (int c = 0; c < 40; c += 8) {
-      const int col = half * 40 + c;  // output column of o[c]
+    for (int c = 0; c < OC; c += 8) {
+      const int col = half * OC + c;  // output column of o[c]
       const uint32_t w0 = pack_bf16x2(o[c] * inv, o[c + 1] * inv), w1 = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
       const uint32_t w2 = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), w3 = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
       if (col < 64) st_shared_v4(swz128(stg64, lane, col >> 3), w0, w1, w2, w3);
       else st_shared_v4(stg16 + lane * 32 + (col - 64) * 2, w0, w1, w2, w3);
     }
     fence_proxy_async_smem();
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");  // both halves of every row are staged
+    if constexpr (TPR == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // both halves of every row are staged
+    else __syncwarp();
     if (half == 0 && lane == 0) {
       const int row0 = tile.q_row0 + t * QT + quad * 32;
       tma_store_2d(&to64, stg64, head * HD, row0);
@@ -915,8 +893,8 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
     }
 #ifdef B200_ATTN_TIMING
     TSTAMP2(0);
-    if (trec) printf("full2 softmax warp %d (%d blocks): other+store %lld | wait_s %lld | pass1 %lld | exch %lld | wait_pv %lld | pass2 %lld | fence+arrive %lld | acc %lld | p1 ld %lld | p2 ld %lld\n",
-                     warp, nblk, tstamp[0], tstamp[1], tstamp[2], tstamp[3], tstamp[7], tstamp[4], tstamp[5], tstamp[6], tstamp[9], tstamp[8]);
+    if (trec) printf("full2 softmax warp %d (%d blocks, %d rescales): other+store %lld | wait_s %lld | pass1 %lld | exch %lld | wait_pv %lld | rescale %lld | pass2 %lld | fence+arrive %lld | final O %lld\n",
+                     warp, nblk, n_rescale, tstamp[0], tstamp[1], tstamp[2], tstamp[3], tstamp[7], tstamp[6], tstamp[4], tstamp[5], tstamp[8]);
 #endif
   }
 
@@ -997,13 +975,23 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
     if (!two_threads) return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
     using L = AttnCfg<2, 2, 1, true>;
     constexpr int kSmem = L::BYTES + 4096;  // + partner-exchange area behind the barriers
+    static int tpr = 0;
+    if (tpr == 0) {
+      const char* e = getenv("B200VIT_ATTN_TPR");
+      tpr = (e != nullptr && e[0] == '1') ? 1 : 2;
+    }
     static DeviceOnce attr;
     if (attr.need()) {
-      B200_CUDA_OK(cudaFuncSetAttribute(attn_full2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      B200_CUDA_OK(cudaFuncSetAttribute(attn_full2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      B200_CUDA_OK(cudaFuncSetAttribute(attn_full2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
       attr.mark();
     }
-    B200_CUDA_OK(launch_kernel(attn_full2_kernel, dim3(n_tiles, heads), dim3(F2_THREADS), kSmem, stream, 1, g.tm64, g.tm16, g.to64,
-                               g.to16, d_tiles, bd, m_rows, heads, scale_log2));
+    if (tpr == 1)
+      B200_CUDA_OK(launch_kernel(attn_full2_kernel<1>, dim3(n_tiles, heads), dim3(96 + 256), kSmem, stream, 1, g.tm64, g.tm16,
+                                 g.to64, g.to16, d_tiles, bd, m_rows, heads, scale_log2));
+    else
+      B200_CUDA_OK(launch_kernel(attn_full2_kernel<2>, dim3(n_tiles, heads), dim3(96 + 512), kSmem, stream, 1, g.tm64, g.tm16,
+                                 g.to64, g.to16, d_tiles, bd, m_rows, heads, scale_log2));
     return 0;
   }
   if (rows_per_tile != 128) return fail(B200VIT_EINVAL, "attention: rows_per_tile must be 128 or 256");
