@@ -533,30 +533,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   }
 }
 
-// ------------------------------------------------------------------ full-attention layers, two threads per row
-// Same pipeline as attn_tc_kernel<2, 2, 1, true> (two 128-row query tiles of one head sharing each K/V block), but the
-// softmax is issue/latency-bound with one thread per row (phase timings: 3.1 k cycles per block and tile), so every row is
-// split between TWO threads (64 score columns / 40 output columns each; 16 softmax warps instead of 8).  The partners
-// exchange their partial row maximum through shared memory once per block and their partial row sums once at the end.
-//
-// O stays in TMEM for the whole K/V walk: P.V(j) accumulates onto P.V(j-1) and the softmax warps never read a per-block
-// O back.  The running maximum is therefore LAZY: a row keeps the maximum m it used so far while the new block's maximum
-// stays below m + 8 (log2 units; P <= 2^8, harmless in bf16 / fp32), and only when it grows past that do the row's two
-// threads rescale their 40 O columns in TMEM (tcgen05.ld -> *2^(m - m') -> tcgen05.st) and their partial sums.  After the
-// first block that is rare, so the per-block chain of a tile is  S wait -> row max -> exp2 pass -> P.V  instead of
-// ... -> O drain (80 FFMA per row) -> P.V, and the O hand-shake (o_empty) is gone.
+// ------------------------------------------------------------------ full-attention layers (persistent)
+// Two 128-row query tiles of one head share each K/V block (as attn_tc_kernel<2, 2, 1, true>), one thread per query row,
+// with four changes that each came out of a measurement:
+//  * O stays in TMEM for the whole K/V walk: P.V(j) accumulates onto P.V(j-1) and the softmax warps never read a
+//    per-block O back.  The running maximum is therefore LAZY: a row keeps the maximum m it has used so far while the
+//    new block's maximum stays below m + 8 (log2 units; P <= 2^8, harmless in bf16 / fp32), and only when it grows past
+//    that does the row's thread rescale its O columns in TMEM (tcgen05.ld -> * 2^(m - m') -> tcgen05.st) and its sum.
+//    After the first block that is rare, so the per-block chain of a tile is  S -> row max -> exp2 pass -> P.V  without
+//    the O drain (80 FFMA per row) and without the O hand-shake.
+//  * a block's 128 scores are read from TMEM ONCE into registers and S(t) is released at once (s_free), so the next
+//    Q.K^T runs underneath the softmax and S(j+1) is waiting when the warps come back; P.V(j-1) is only waited for
+//    after the whole exp2 pass, just before P is overwritten.
+//  * one MMA-issuing warp per tile on blocking (hardware-suspended) mbarrier waits.  (A single issuer polling both tiles
+//    with nanosleep between probes reacted late: the sleep quantum is ~1 us.)
+//  * PERSISTENT: one CTA per SM walks work items (256-row tile pair, head), item = blockIdx.x + k * gridDim.x, tile
+//    index fastest (co-resident CTAs share a head's K/V in L2).  Barrier phases run on global block / item counters, so
+//    the K/V ring, S and P flow straight across item boundaries: the next item's Q is loaded as soon as the last Q.K^T
+//    of the current one has been issued, its first Q.K^T runs underneath the current item's last softmax, and an item's
+//    output store drains while the next item's first block is computed.
 constexpr float RESCALE_LOG2 = 8.f;
-#ifndef B200_ATTN_DBG
-#define B200_ATTN_DBG 0
-#endif
-// TPR = threads per query row (2: as described above; 1: one thread owns the whole row -- 8 softmax warps, no partner
-// exchange, 128 score registers).
-template <int TPR>
-__global__ void __launch_bounds__(96 + 256 * TPR, 1)
-attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
+constexpr int F_THREADS = 96 + 256;  // loader, two MMA issuers, 2 x 4 softmax warps
+__global__ void __launch_bounds__(F_THREADS, 1)
+attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                   const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap to16,
-                  const AttnTile* __restrict__ tiles, const int2* __restrict__ bounds, int m_rows, int heads,
-                  float scale_log2) {
+                  const AttnTile* __restrict__ tiles, int n_tiles, const int2* __restrict__ bounds, int m_rows, int heads,
+                  float scale_log2, int mufu_token) {
   using L = AttnCfg<2, 2, 1, true>;
   constexpr int NKV = 2;
   griddep_launch_dependents();
@@ -564,22 +566,20 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
+  uint64_t* q_empty = bars + 1;   // both tiles' last Q.K^T of an item have finished reading Q
+  uint64_t* k_full = bars + 2;
   uint64_t* k_empty = k_full + NKV;
   uint64_t* v_full = k_empty + NKV;
   uint64_t* v_empty = v_full + NKV;
   uint64_t* s_full = v_empty + NKV;  // [2]
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = p_full + 2;
-  uint64_t* s_free = o_full + 2;  // [2] softmax(t, j) holds S(t) in registers: Q.K^T(j+1) may overwrite it
+  uint64_t* s_free = o_full + 2;  // [2] softmax(t, g) holds S(t) in registers: the next Q.K^T may overwrite it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
-  float* exch = reinterpret_cast<float*>(smem + L::OFF_BAR + 256);  // [2 parities][2 tiles][2 halves][128] floats = 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const AttnTile tile = tiles[blockIdx.x];
-  const int head = blockIdx.y;
   const int D = heads * HD;
-  const int nblk = tile.n_kv_blocks;
+  const int n_items = n_tiles * heads;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm64);
@@ -587,6 +587,7 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
     tma_prefetch_desc(&to64);
     tma_prefetch_desc(&to16);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);
     for (int b = 0; b < NKV; ++b) {
       mbar_init(&k_full[b], 1);
       mbar_init(&k_empty[b], 2);  // one commit per tile's issuing warp
@@ -595,9 +596,9 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128 * TPR);
+      mbar_init(&p_full[t], 128);
       mbar_init(&o_full[t], 1);
-      mbar_init(&s_free[t], 128 * TPR);
+      mbar_init(&s_free[t], 128);
     }
     fence_barrier_init();
   }
@@ -613,6 +614,7 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
+      // ===================== TMA loader =====================
       auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
         tma_load_2d(dst, &tm64, bar, col, row);
         tma_load_2d(dst + T64_BYTES, &tm16, bar, col + 64, row);
@@ -621,280 +623,299 @@ attn_full2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constan
         tma_load_2d(dst, &tm64, bar, col, row);
         tma_load_2d(dst + T64_BYTES, &tm64, bar, col + 64, row);
       };
-      mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-      for (int t = 0; t < 2; ++t) load_tile(smem + L::OFF_Q + t * TILE_BYTES, q_full, head * HD, tile.q_row0 + t * QT);
-      for (int j = 0; j < nblk; ++j) {
-        const int b = j % NKV;
-        const uint32_t par = ((j / NKV) & 1) ^ 1;
-        const int row = tile.kv_row0 + j * KVB;
-        mbar_wait(&k_empty[b], par);
-        mbar_arrive_expect_tx(&k_full[b], TILE_BYTES);
-        load_tile(smem + L::OFF_K + b * TILE_BYTES, &k_full[b], D + head * HD, row);
-        mbar_wait(&v_empty[b], par);
-        mbar_arrive_expect_tx(&v_full[b], V_TILE_BYTES);
-        load_v(smem + L::OFF_V + b * V_TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
+      int g = 0, n = 0;  // global K/V block and item ordinals of this CTA
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const AttnTile tile = tiles[item % n_tiles];
+        const int head = item / n_tiles;
+        mbar_wait(q_empty, (n & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+        for (int t = 0; t < 2; ++t) load_tile(smem + L::OFF_Q + t * TILE_BYTES, q_full, head * HD, tile.q_row0 + t * QT);
+        for (int j = 0; j < tile.n_kv_blocks; ++j, ++g) {
+          const int b = g % NKV;
+          const uint32_t par = ((g / NKV) & 1) ^ 1;
+          const int row = tile.kv_row0 + j * KVB;
+          mbar_wait(&k_empty[b], par);
+          mbar_arrive_expect_tx(&k_full[b], TILE_BYTES);
+          load_tile(smem + L::OFF_K + b * TILE_BYTES, &k_full[b], D + head * HD, row);
+          mbar_wait(&v_empty[b], par);
+          mbar_arrive_expect_tx(&v_full[b], V_TILE_BYTES);
+          load_v(smem + L::OFF_V + b * V_TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
+        }
       }
     }
   } else if (warp <= 2) {
     if (lane == 0) {
+      // ===================== MMA issuers: one warp per query tile =====================
+      // Each walks its own tile's fixed order   Q.K^T(0);  for every block g: [S(t) read by softmax(g): Q.K^T(g+1)]
+      // [P(t, g) written: P.V(g)]   on blocking (hardware-suspended) mbarrier waits, straight across item boundaries.  The
+      // softmax warps release S(t) as soon as a block's scores are in their registers, so Q.K^T(g+1) runs underneath
+      // softmax(g) and S(g+1) is waiting when they come back.  (A single issuer polling both tiles with nanosleep between
+      // probes reacted late: the sleep quantum is ~1 us.)  The tensor pipe interleaves the two tiles' MMAs in arrival
+      // order; a K/V stage / the Q buffer is released when BOTH warps have committed their use of it (count 2).
       constexpr uint32_t idesc_qk = idesc_bf16(QT, KVB, false);
       constexpr uint32_t idesc_pv = idesc_bf16(QT, HD, true);
-      auto issue_qk = [&](int t, int i) {
+      const int t = warp - 1;
+      auto issue_qk = [&](int g) {
         const uint32_t q64 = smem_u32(smem + L::OFF_Q + t * TILE_BYTES), q16 = q64 + T64_BYTES;
-        const uint32_t k64 = smem_u32(smem + L::OFF_K + (i % NKV) * TILE_BYTES), k16 = k64 + T64_BYTES;
+        const uint32_t k64 = smem_u32(smem + L::OFF_K + (g % NKV) * TILE_BYTES), k16 = k64 + T64_BYTES;
         const uint32_t ts = tmem_base + L::S_COL(t);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(ts, umma_desc_k128(q64 + k * 32), umma_desc_k128(k64 + k * 32), idesc_qk, k != 0 ? 1u : 0u);
         umma_bf16_ss(ts, desc_k_sw32(q16), desc_k_sw32(k16), idesc_qk, 1u);
         umma_commit(&s_full[t]);
+        umma_commit(&k_empty[g % NKV]);
       };
-      auto issue_pv = [&](int t, int i) {  // O(t) += P(t) V(i): the softmax warps rescale O themselves when a row maximum grows
-        mbar_wait(&p_full[t], i & 1);
-        tc_fence_after();
+      auto issue_pv = [&](int g, bool first) {  // O(t) (+)= P(t) V(g): the softmax warps rescale O themselves when a row maximum grows
         const uint32_t p0 = smem_u32(smem + L::OFF_P + t * P_BYTES);
-        const uint32_t v64 = smem_u32(smem + L::OFF_V + (i % NKV) * V_TILE_BYTES);
+        const uint32_t v64 = smem_u32(smem + L::OFF_V + (g % NKV) * V_TILE_BYTES);
         const uint32_t to = tmem_base + L::O_COL(t);
-#if B200_ATTN_DBG == 2
-        if (i == 0)
-#endif
 #pragma unroll
         for (int k = 0; k < KVB / 16; ++k) {
           const uint64_t pa = umma_desc_k128(p0 + (k >> 2) * T64_BYTES + (k & 3) * 32);
-          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv, (i != 0 || k != 0) ? 1u : 0u);
+          umma_bf16_ss(to, pa, desc_mn_sw128(v64 + k * 2048), idesc_pv, (!first || k != 0) ? 1u : 0u);
         }
         umma_commit(&o_full[t]);
+        umma_commit(&v_empty[g % NKV]);
       };
-      // One issuing warp per query tile, each walking its own tile's fixed order
-      //     Q.K^T(0);  for i: [S(t) read by softmax(i): Q.K^T(i+1)]  [P(t, i) written: P.V(i)]
-      // on blocking (hardware-suspended) mbarrier waits: the softmax warps release S(t) as soon as a block's scores are
-      // in their registers, so Q.K^T(i+1) runs underneath softmax(i) and S(i+1) is waiting when they come back.  (A single
-      // issuer polling both tiles with nanosleep between probes reacted a block period late: the sleep quantum is ~1 us.)
-      // The tensor pipe interleaves the two tiles' MMAs in arrival order; a K/V stage is released when BOTH tiles' warps
-      // have committed their use of it (k_empty / v_empty count 2).
-      const int t = warp - 1;
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(t, 0);
-      umma_commit(&k_empty[0]);
-      for (int i = 0; i < nblk; ++i) {
-        if (i + 1 < nblk) {
-          mbar_wait(&s_free[t], i & 1);
-          mbar_wait(&k_full[(i + 1) % NKV], ((i + 1) / NKV) & 1);
-          tc_fence_after();
-          issue_qk(t, i + 1);
-          umma_commit(&k_empty[(i + 1) % NKV]);
+      int g = 0, n = 0;
+      int item = blockIdx.x;
+      if (item < n_items) {
+        int nblk = tiles[item % n_tiles].n_kv_blocks;
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        issue_qk(0);
+        if (nblk == 1) umma_commit(q_empty);
+        while (item < n_items) {
+          const int next_item = item + gridDim.x;
+          const int next_nblk = next_item < n_items ? tiles[next_item % n_tiles].n_kv_blocks : 0;
+          for (int i = 0; i < nblk; ++i, ++g) {
+            // the successor block's Q.K^T first: it only needs S(t) back, not P(t, g)
+            const bool in_item = i + 1 < nblk;
+            if (in_item || next_nblk > 0) {
+              mbar_wait(&s_free[t], g & 1);
+              if (!in_item) mbar_wait(q_full, (n + 1) & 1);
+              mbar_wait(&k_full[(g + 1) % NKV], ((g + 1) / NKV) & 1);
+              tc_fence_after();
+              issue_qk(g + 1);
+              if (in_item ? (i + 2 == nblk) : (next_nblk == 1)) umma_commit(q_empty);  // that was the last Q.K^T of its item
+            }
+            mbar_wait(&v_full[g % NKV], (g / NKV) & 1);
+            mbar_wait(&p_full[t], g & 1);
+            tc_fence_after();
+            issue_pv(g, i == 0);
+          }
+          item = next_item;
+          nblk = next_nblk;
+          ++n;
         }
-        mbar_wait(&v_full[i % NKV], (i / NKV) & 1);
-        issue_pv(t, i);  // waits for p_full(t, i)
-        umma_commit(&v_empty[i % NKV]);
       }
     }
   } else {
-    // ===================== softmax + accumulation: two threads per query row =====================
-    constexpr int SC = 128 / TPR;  // score columns per thread
-    constexpr int OC = HD / TPR;   // output columns per thread
+    // ===================== softmax: one thread per query row =====================
+    constexpr int SC = KVB;  // score columns per thread
+    constexpr int OC = HD;   // output columns per thread
     const int sw = warp - 3;
-    const int t = sw / (4 * TPR);               // query tile
-    const int half = TPR == 2 ? (sw >> 2) & 1 : 0;  // score columns [SC*half, +SC), output columns [OC*half, +OC)
+    const int t = sw >> 2;          // query tile
     const int quad = warp & 3;      // TMEM lane quadrant
     const int r = quad * 32 + lane;
-    const int row = tile.q_row0 + t * QT + r;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t ts = lane_base + L::S_COL(t) + half * SC;
-    const uint32_t to = lane_base + L::O_COL(t) + half * OC;
-    const uint32_t psub = smem_u32(smem + L::OFF_P + t * P_BYTES) + half * T64_BYTES;  // this thread's first 64-wide P sub-tile
-    const int pair_bar = 3 + t * 4 + quad;  // the two warps that share this tile's rows [32 quad, +32): partner exchange
-    int2 bd = make_int2(0, 0);
-    if (row < m_rows) bd = bounds[row];
-    float m_used = -INFINITY, l_part = 0.f;  // the maximum the row's probabilities are currently expressed against
+    const uint32_t ts = lane_base + L::S_COL(t);
+    const uint32_t to = lane_base + L::O_COL(t);
+    const uint32_t pbuf = smem_u32(smem + L::OFF_P + t * P_BYTES);
+    const uint32_t stg64 = pbuf + quad * 4096;              // output staging [32 rows x 64 cols], SWIZZLE_128B
+    const uint32_t stg16 = pbuf + T64_BYTES + quad * 4096;  // output staging [32 rows x 16 cols], dense
+    const int tok_mine = 3 + t * 4 + quad, tok_other = 3 + (t ^ 1) * 4 + quad;  // named barriers: MUFU token (below)
+    int g = 0;   // global block ordinal (barrier phases)
 #ifdef B200_ATTN_TIMING
     long long tstamp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
-    const bool trec = (blockIdx.x == 1 && blockIdx.y == 0 && (warp == 3 || warp == 3 + 4 * TPR) && lane == 0);
-    int n_rescale = 0;
+    const bool trec = (blockIdx.x == 1 && (warp == 3 || warp == 7) && lane == 0);
+    int n_rescale = 0, n_blocks = 0;
 #define TSTAMP2(k) do { long long _n = clock64(); tstamp[k] += _n - tprev; tprev = _n; } while (0)
 #else
 #define TSTAMP2(k)
 #endif
 
-    for (int j = 0; j < nblk; ++j) {
-      TSTAMP2(0);
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      TSTAMP2(1);
-      const int kv0 = tile.kv_row0 + j * KVB + half * SC;            // first kv row of this thread's columns
-      const int lo = max(bd.x - kv0, 0), hi = min(bd.y - kv0, SC);   // valid columns among them
-      // this thread's share of the S(t) row into registers, then S(t) is free for Q.K^T(j+1)
-      uint32_t sv[SC];
-#pragma unroll
-      for (int c = 0; c < SC; c += 32) tmem_ld32(ts + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_free[t]);
-      const bool all_valid = __all_sync(0xffffffffu, lo == 0 && hi == SC);
-      float mx;
-      if (all_valid) {
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (fmax3 pairs them up)
-#pragma unroll
-        for (int i = 0; i < SC; i += 4) {
-          m4[0] = fmaxf(m4[0], __uint_as_float(sv[i]));
-          m4[1] = fmaxf(m4[1], __uint_as_float(sv[i + 1]));
-          m4[2] = fmaxf(m4[2], __uint_as_float(sv[i + 2]));
-          m4[3] = fmaxf(m4[3], __uint_as_float(sv[i + 3]));
-        }
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      } else {
-        mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < SC; ++i) mx = fmaxf(mx, (i >= lo && i < hi) ? __uint_as_float(sv[i]) : -INFINITY);
-      }
-      TSTAMP2(2);
-      if constexpr (TPR == 2) {  // partner exchange of the partial row maximum (double-buffered by block parity)
-        float* ex = exch + ((j & 1) * 2 + t) * 256;
-        ex[half * 128 + r] = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        mx = fmaxf(mx, ex[(half ^ 1) * 128 + r]);
-      }
-      TSTAMP2(3);
-      // lazy maximum: both partners see the same mx, so they take the same decision
-      const float m_blk = mx * scale_log2;
-      const bool grow = m_blk > m_used + RESCALE_LOG2;  // also the first block with a valid column (m_used = -inf)
-      float alpha = 1.f;
-      if (grow) {
-        alpha = ex2_approx(m_used - m_blk);  // m_used = -inf -> 0
-        m_used = m_blk;
-      }
-      const float m_use = (m_used == -INFINITY) ? 0.f : m_used;  // nothing valid so far: p = 0, no NaN
-      l_part *= alpha;
-      float sum = 0.f;
-      uint32_t pk[SC / 2];  // this thread's probabilities, bf16
-#pragma unroll
-      for (int c = 0; c < SC; c += 32) {
-        if (all_valid) {
-          // packed fp32x2 FFMA / FADD: two lanes per issue slot for everything except the MUFU itself
-          const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), nm2 = f32x2_pack(-m_use, -m_use);
-          uint64_t s2a = 0ull, s2b = 0ull;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float x0, x1, x2, x3;
-            f32x2_unpack(f32x2_fma(f32x2_pack_bits(sv[c + i], sv[c + i + 1]), sc2, nm2), x0, x1);
-            f32x2_unpack(f32x2_fma(f32x2_pack_bits(sv[c + i + 2], sv[c + i + 3]), sc2, nm2), x2, x3);
-#if B200_ATTN_DBG == 1
-            const float p0 = x0 * 0.001f, p1 = x1 * 0.001f, p2 = x2 * 0.001f, p3 = x3 * 0.001f;
-#else
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
-#endif
-            s2a = f32x2_add(s2a, f32x2_pack(p0, p1));
-            s2b = f32x2_add(s2b, f32x2_pack(p2, p3));
-            pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
-            pk[((c + i) >> 1) + 1] = pack_bf16x2(p2, p3);
-          }
-          float sa, sb, sc, sd;
-          f32x2_unpack(s2a, sa, sb);
-          f32x2_unpack(s2b, sc, sd);
-          sum += (sa + sb) + (sc + sd);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(__uint_as_float(sv[c + i]) * scale_log2 - m_use);
-            float p1 = ex2_approx(__uint_as_float(sv[c + i + 1]) * scale_log2 - m_use);
-            p0 = (c + i >= lo && c + i < hi) ? p0 : 0.f;
-            p1 = (c + i + 1 >= lo && c + i + 1 < hi) ? p1 : 0.f;
-            sum += p0 + p1;
-            pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
-          }
-        }
-      }
-      if (j >= 1) {
-        // every probability of the block is computed: only now is P.V(j-1) needed (P may be overwritten, O is at rest)
-        TSTAMP2(4);
-        mbar_wait(&o_full[t], (j - 1) & 1);
-        TSTAMP2(7);
-        if (__any_sync(0xffffffffu, grow)) {  // rare after the first block: O(row) *= 2^(m_old - m_new) in TMEM
-          tc_fence_after();
-#pragma unroll
-          for (int c0 = 0; c0 < OC; c0 += 40) {  // 40 columns (32 + 8) per trip
-            uint32_t v[32], v8[8];
-            tmem_ld32(to + c0, v);
-            tmem_ld8(to + c0 + 32, v8);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v8[i] = __float_as_uint(__uint_as_float(v8[i]) * alpha);
-            tmem_st32(to + c0, v);
-            tmem_st8(to + c0 + 32, v8);
-          }
-          tmem_st_wait();
-#ifdef B200_ATTN_TIMING
-          ++n_rescale;
-#endif
-        }
-        TSTAMP2(6);
-      }
-#pragma unroll
-      for (int q = 0; q < SC / 8; ++q)  // 16-byte chunk q of this thread's columns: sub-tile q / 8, chunk q % 8
-        st_shared_v4(swz128(psub + (q >> 3) * T64_BYTES, r, q & 7), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      l_part += sum;
-      TSTAMP2(4);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
-      TSTAMP2(5);
-    }
-    // the finished O of this thread's 40 columns
-    mbar_wait(&o_full[t], (nblk - 1) & 1);
-    tc_fence_after();
-    float o[OC];
-#pragma unroll
-    for (int c0 = 0; c0 < OC; c0 += 40) {
-      uint32_t v[32], v8[8];
-      tmem_ld32(to + c0, v);
-      tmem_ld8(to + c0 + 32, v8);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[c0 + i] = __uint_as_float(v[i]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[c0 + 32 + i] = __uint_as_float(v8[i]);
-    }
-    TSTAMP2(8);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const AttnTile tile = tiles[item % n_tiles];
+      const int head = item / n_tiles;
+      const int nblk = tile.n_kv_blocks;
+      const int row = tile.q_row0 + t * QT + r;
+      int2 bd = make_int2(0, 0);
+      if (row < m_rows) bd = bounds[row];
+      float m_used = -INFINITY, l_part = 0.f;  // the maximum the row's probabilities are currently expressed against
 
-    // combine the partners' partial row sums, then stage O (bf16) in this warp's own rows of the idle P buffer
-    float l = l_part;
-    if constexpr (TPR == 2) {
-      float* ex = exch + ((nblk & 1) * 2 + t) * 256;
-      ex[half * 128 + r] = l_part;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      l += ex[(half ^ 1) * 128 + r];
-    }
-    const float inv = (l > 0.f) ? 1.f / l : 0.f;
-    const uint32_t pbuf = smem_u32(smem + L::OFF_P + t * P_BYTES);
-    const uint32_t stg64 = pbuf + quad * 4096;              // [32 rows x 64 cols], SWIZZLE_128B
-    const uint32_t stg16 = pbuf + T64_BYTES + quad * 4096;  // [32 rows x 16 cols], dense
+      for (int j = 0; j < nblk; ++j, ++g) {
+        TSTAMP2(0);
+        mbar_wait(&s_full[t], g & 1);
+        tc_fence_after();
+        TSTAMP2(1);
+        const int kv0 = tile.kv_row0 + j * KVB;                        // first kv row of the block
+        const int lo = max(bd.x - kv0, 0), hi = min(bd.y - kv0, SC);   // this row's valid columns
+        // the S(t) row into registers, then S(t) is free for the next Q.K^T
+        uint32_t sv[SC];
 #pragma unroll
-    for (int c = 0; c < OC; c += 8) {
-      const int col = half * OC + c;  // output column of o[c]
-      const uint32_t w0 = pack_bf16x2(o[c] * inv, o[c + 1] * inv), w1 = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
-      const uint32_t w2 = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), w3 = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
-      if (col < 64) st_shared_v4(swz128(stg64, lane, col >> 3), w0, w1, w2, w3);
-      else st_shared_v4(stg16 + lane * 32 + (col - 64) * 2, w0, w1, w2, w3);
-    }
-    fence_proxy_async_smem();
-    if constexpr (TPR == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // both halves of every row are staged
-    else __syncwarp();
-    if (half == 0 && lane == 0) {
-      const int row0 = tile.q_row0 + t * QT + quad * 32;
-      tma_store_2d(&to64, stg64, head * HD, row0);
-      tma_store_2d(&to16, stg16, head * HD + 64, row0);
-      bulk_commit();
-      bulk_wait<0>();
-    }
+        for (int c = 0; c < SC; c += 32) tmem_ld32(ts + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+        const bool all_valid = __all_sync(0xffffffffu, lo == 0 && hi == SC);
+        float mx;
+        if (all_valid) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (fmax3 pairs them up)
+#pragma unroll
+          for (int i = 0; i < SC; i += 4) {
+            m4[0] = fmaxf(m4[0], __uint_as_float(sv[i]));
+            m4[1] = fmaxf(m4[1], __uint_as_float(sv[i + 1]));
+            m4[2] = fmaxf(m4[2], __uint_as_float(sv[i + 2]));
+            m4[3] = fmaxf(m4[3], __uint_as_float(sv[i + 3]));
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        } else {
+          mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < SC; ++i) mx = fmaxf(mx, (i >= lo && i < hi) ? __uint_as_float(sv[i]) : -INFINITY);
+        }
+        TSTAMP2(2);
+        // lazy maximum
+        const float m_blk = mx * scale_log2;
+        const bool grow = m_blk > m_used + RESCALE_LOG2;  // also the first block with a valid column (m_used = -inf)
+        float alpha = 1.f;
+        if (grow) {
+          alpha = ex2_approx(m_used - m_blk);  // m_used = -inf -> 0
+          m_used = m_blk;
+        }
+        const float m_use = (m_used == -INFINITY) ? 0.f : m_used;  // nothing valid so far: p = 0, no NaN
+        l_part *= alpha;
+        float sum = 0.f;
+        uint32_t pk[SC / 2];  // this thread's probabilities, bf16
+        // MUFU token of the sub-partition.  Its two softmax warps (one per query tile) otherwise drift into lockstep: both
+        // in the exp2 pass at once, sharing the one MUFU, then both in their MUFU-free phases with the unit idle (ncu:
+        // 47 % of their samples on MUFU.EX2, the pipe 45 % busy).  Alternating, one warp's exp2 pass runs underneath the
+        // other's P store / S load / row maximum.  Worth 3 % -- a single warp cannot keep the MUFU full either.
+        if (mufu_token && (t == 1 || g > 0)) named_barrier(tok_mine, 64);
+#pragma unroll
+        for (int c = 0; c < SC; c += 32) {
+          if (all_valid) {
+            // packed fp32x2 FFMA / FADD: two lanes per issue slot for everything except the MUFU itself
+            const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), nm2 = f32x2_pack(-m_use, -m_use);
+            uint64_t s2a = 0ull, s2b = 0ull;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float x0, x1, x2, x3;
+              f32x2_unpack(f32x2_fma(f32x2_pack_bits(sv[c + i], sv[c + i + 1]), sc2, nm2), x0, x1);
+              f32x2_unpack(f32x2_fma(f32x2_pack_bits(sv[c + i + 2], sv[c + i + 3]), sc2, nm2), x2, x3);
+              const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+              s2a = f32x2_add(s2a, f32x2_pack(p0, p1));
+              s2b = f32x2_add(s2b, f32x2_pack(p2, p3));
+              pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
+              pk[((c + i) >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+            float sa, sb, sc, sd;
+            f32x2_unpack(s2a, sa, sb);
+            f32x2_unpack(s2b, sc, sd);
+            sum += (sa + sb) + (sc + sd);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = ex2_approx(__uint_as_float(sv[c + i]) * scale_log2 - m_use);
+              float p1 = ex2_approx(__uint_as_float(sv[c + i + 1]) * scale_log2 - m_use);
+              p0 = (c + i >= lo && c + i < hi) ? p0 : 0.f;
+              p1 = (c + i + 1 >= lo && c + i + 1 < hi) ? p1 : 0.f;
+              sum += p0 + p1;
+              pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
+            }
+          }
+        }
+        // hand the token over; tile 1's very last pass has nobody left to hand it to
+        if (mufu_token && !(t == 1 && j + 1 == nblk && item + static_cast<int>(gridDim.x) >= n_items))
+          asm volatile("bar.arrive %0, 64;" ::"r"(tok_other) : "memory");
+        TSTAMP2(4);
+        if (j >= 1) {
+          // every probability of the block is computed: only now is P.V(g-1) needed (P may be overwritten, O is at rest)
+          mbar_wait(&o_full[t], (g - 1) & 1);
+          TSTAMP2(7);
+          if (__any_sync(0xffffffffu, grow)) {  // rare after the first block: O(row) *= 2^(m_old - m_new) in TMEM
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < OC; c0 += 40) {  // 40 columns (32 + 8) per trip
+              uint32_t v[32], v8[8];
+              tmem_ld32(to + c0, v);
+              tmem_ld8(to + c0 + 32, v8);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] = __float_as_uint(__uint_as_float(v8[i]) * alpha);
+              tmem_st32(to + c0, v);
+              tmem_st8(to + c0 + 32, v8);
+            }
+            tmem_st_wait();
 #ifdef B200_ATTN_TIMING
-    TSTAMP2(0);
-    if (trec) printf("full2 softmax warp %d (%d blocks, %d rescales): other+store %lld | wait_s %lld | pass1 %lld | exch %lld | wait_pv %lld | rescale %lld | pass2 %lld | fence+arrive %lld | final O %lld\n",
-                     warp, nblk, n_rescale, tstamp[0], tstamp[1], tstamp[2], tstamp[3], tstamp[7], tstamp[6], tstamp[4], tstamp[5], tstamp[8]);
+            ++n_rescale;
+#endif
+          }
+          TSTAMP2(6);
+        } else if (g > 0) {
+          // first block of a later item: the previous item's output store (staged in this warp's rows of the P region)
+          // must have been read out of shared memory
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < SC / 8; ++q)  // 16-byte chunk q of this thread's columns: sub-tile q / 8, chunk q % 8
+          st_shared_v4(swz128(pbuf + (q >> 3) * T64_BYTES, r, q & 7), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        l_part += sum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        TSTAMP2(5);
+#ifdef B200_ATTN_TIMING
+        ++n_blocks;
+#endif
+      }
+      // the finished O of this thread's columns
+      mbar_wait(&o_full[t], (g - 1) & 1);
+      tc_fence_after();
+      float o[OC];
+#pragma unroll
+      for (int c0 = 0; c0 < OC; c0 += 40) {
+        uint32_t v[32], v8[8];
+        tmem_ld32(to + c0, v);
+        tmem_ld8(to + c0 + 32, v8);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c0 + i] = __uint_as_float(v[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[c0 + 32 + i] = __uint_as_float(v8[i]);
+      }
+      TSTAMP2(8);
+      // stage O (bf16) in this warp's own rows of the idle P buffer
+      const float inv = (l_part > 0.f) ? 1.f / l_part : 0.f;
+#pragma unroll
+      for (int c = 0; c < OC; c += 8) {
+        const int col = c;
+        const uint32_t w0 = pack_bf16x2(o[c] * inv, o[c + 1] * inv), w1 = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+        const uint32_t w2 = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv), w3 = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+        if (col < 64) st_shared_v4(swz128(stg64, lane, col >> 3), w0, w1, w2, w3);
+        else st_shared_v4(stg16 + lane * 32 + (col - 64) * 2, w0, w1, w2, w3);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = tile.q_row0 + t * QT + quad * 32;
+        tma_store_2d(&to64, stg64, head * HD, row0);  // rows >= m_rows are clipped by the tensor map
+        tma_store_2d(&to16, stg16, head * HD + 64, row0);
+        bulk_commit();
+      }
+      TSTAMP2(0);
+    }  // items of this CTA
+    if (lane == 0) bulk_wait<0>();  // output stores have landed before the CTA exits
+#ifdef B200_ATTN_TIMING
+    if (trec) printf("full attention softmax warp %d (%d blocks, %d rescales): other+store %lld | wait_s %lld | ld+max %lld | - %lld | exps %lld | wait_pv %lld | rescale %lld | store+arrive %lld | final O %lld\n",
+                     warp, n_blocks, n_rescale, tstamp[0], tstamp[1], tstamp[2], tstamp[3], tstamp[4], tstamp[7], tstamp[6], tstamp[5], tstamp[8]);
 #endif
   }
 
@@ -967,31 +988,24 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int2* bd = reinterpret_cast<const int2*>(d_bounds);
   if (rows_per_tile == 256) {
-    static int two_threads = -1;
-    if (two_threads < 0) {
-      const char* e = getenv("B200VIT_ATTN_FULL2");
-      two_threads = (e == nullptr || e[0] != '0') ? 1 : 0;
+    static int generic = -1, token = -1;
+    if (generic < 0) {
+      const char* e = getenv("B200VIT_ATTN_FULL_GENERIC");  // debugging: the generic kernel's two-tile variant
+      generic = (e != nullptr && e[0] == '1') ? 1 : 0;
+      e = getenv("B200VIT_ATTN_TOKEN");
+      token = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
-    if (!two_threads) return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
+    if (generic) return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
     using L = AttnCfg<2, 2, 1, true>;
-    constexpr int kSmem = L::BYTES + 4096;  // + partner-exchange area behind the barriers
-    static int tpr = 0;
-    if (tpr == 0) {
-      const char* e = getenv("B200VIT_ATTN_TPR");
-      tpr = (e != nullptr && e[0] == '1') ? 1 : 2;
-    }
     static DeviceOnce attr;
     if (attr.need()) {
-      B200_CUDA_OK(cudaFuncSetAttribute(attn_full2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-      B200_CUDA_OK(cudaFuncSetAttribute(attn_full2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      B200_CUDA_OK(cudaFuncSetAttribute(attn_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
       attr.mark();
     }
-    if (tpr == 1)
-      B200_CUDA_OK(launch_kernel(attn_full2_kernel<1>, dim3(n_tiles, heads), dim3(96 + 256), kSmem, stream, 1, g.tm64, g.tm16,
-                                 g.to64, g.to16, d_tiles, bd, m_rows, heads, scale_log2));
-    else
-      B200_CUDA_OK(launch_kernel(attn_full2_kernel<2>, dim3(n_tiles, heads), dim3(96 + 512), kSmem, stream, 1, g.tm64, g.tm16,
-                                 g.to64, g.to16, d_tiles, bd, m_rows, heads, scale_log2));
+    const int n_items = n_tiles * heads;
+    const int grid = n_items < device_sm_count() ? n_items : device_sm_count();  // persistent: one CTA per SM
+    B200_CUDA_OK(launch_kernel(attn_full_kernel, dim3(grid), dim3(F_THREADS), L::BYTES, stream, 1, g.tm64, g.tm16, g.to64, g.to16,
+                               d_tiles, n_tiles, bd, m_rows, heads, scale_log2, token));
     return 0;
   }
   if (rows_per_tile != 128) return fail(B200VIT_EINVAL, "attention: rows_per_tile must be 128 or 256");

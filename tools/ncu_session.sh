@@ -5,7 +5,7 @@
 TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
-KREGEX='regex:gemm_tcgen05|attn_tc|attn_full2|rmsnorm_kernel|overlay_patchify|cast_bf16|raster_kernel'
+KREGEX='regex:gemm_tcgen05|attn_tc|attn_full_kernel|rmsnorm_kernel|overlay_patchify|cast_bf16|raster_kernel'
 if [ -z "$ONLY_CAPS" ]; then
 # ---- launch list: skip the warm-up forwards (138 launches each incl. none from torch), take two forwards
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 552 -c 276 --csv --log-file $OUT/${TAG}_launches.csv \
@@ -39,7 +39,7 @@ cap qkv 'gemm_tcgen05' 8 python tools/prof_gemm.py qkv 2
 cap proj 'gemm_tcgen05' 8 python tools/prof_gemm.py proj 2
 cap down 'gemm_tcgen05' 8 python tools/prof_gemm.py down 2
 if [ -z "$ONLY_CAPS" ]; then
-cap attn_full 'attn_full2' 4 python tools/prof_attn.py 1024 2
+cap attn_full 'attn_full_kernel' 4 python tools/prof_attn.py 1024 2
 cap overlay 'overlay_patchify' 6 python tools/prof_overlay.py
 fi
 ls -la $OUT | grep ${TAG}_ | head -40
