@@ -680,6 +680,10 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       };
       int g = 0, n = 0;
       int item = blockIdx.x;
+#ifdef B200_ATTN_MMA_PROBE
+      long long probe_issue = 0, probe_done = 0;
+      int probe_n = 0;
+#endif
       if (item < n_items) {
         int nblk = tiles[item % n_tiles].n_kv_blocks;
         mbar_wait(q_full, 0);
@@ -704,13 +708,25 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
             mbar_wait(&v_full[g % NKV], (g / NKV) & 1);
             mbar_wait(&p_full[t], g & 1);
             tc_fence_after();
+#ifdef B200_ATTN_MMA_PROBE
+            const long long c0 = clock64();
             issue_pv(g, i == 0);
+            const long long c1 = clock64();
+            mbar_wait(&o_full[t], g & 1);
+            const long long c2 = clock64();
+            probe_issue += c1 - c0, probe_done += c2 - c0, ++probe_n;
+#else
+            issue_pv(g, i == 0);
+#endif
           }
           item = next_item;
           nblk = next_nblk;
           ++n;
         }
       }
+#ifdef B200_ATTN_MMA_PROBE
+      if (blockIdx.x == 1) printf("mma warp %d: P.V issue %lld cycles, issue->complete %lld cycles (avg of %d)\n", t, probe_issue / probe_n, probe_done / probe_n, probe_n);
+#endif
     }
   } else {
     // ===================== softmax: one thread per query row =====================
