@@ -502,6 +502,7 @@ int b200vit_forward(const b200vit_plan* p, const b200vit_weights* w, const void*
   g.m = M, g.n = D, g.k = p->kpe, g.ldo = D, g.epilogue = B200VIT_EPI_STORE_F32;
   if ((rc = gemm(B200VIT_K_PATCH_EMBED))) return rc;
 
+  int n_full_seen = 0;
   for (int l = 0; l < c.depth; ++l) {
     const b200vit_layer_weights& lw = w->layers[l];
     const bool full = is_fullatt(c, l);
@@ -517,10 +518,13 @@ int b200vit_forward(const b200vit_plan* p, const b200vit_weights* w, const void*
     } else {
       if ((rc = gemm(B200VIT_K_QKV))) return rc;
       prof.begin(full ? B200VIT_K_ATTN_FULL : B200VIT_K_ATTN_WINDOW);
+      // full layers draw their work items from a counter in the tail of the (zeroed) sync scratch, one per layer
+      int32_t* counter = (full && n_full_seen < 64) ? sync + (B200VIT_GEMM_SYNC_INTS - 64) + n_full_seen : nullptr;
+      if (full) ++n_full_seen;
       rc = launch_attention_tc(qkv, attn, full ? p->d_tiles_full : p->d_tiles_window,
                                static_cast<int>(full ? p->tiles_full.size() : p->tiles_window.size()), full ? 256 : 128,
                                full ? p->maxblk_full : p->maxblk_window, full ? p->d_bounds_full : p->d_bounds_window, M,
-                               c.heads, stream, &cc->attn);
+                               c.heads, stream, &cc->attn, counter);
       if (rc) return rc;
       prof.end();
     }

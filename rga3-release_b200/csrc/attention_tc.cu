@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                   const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap to16,
                   const AttnTile* __restrict__ tiles, int n_tiles, const int2* __restrict__ bounds, int m_rows, int heads,
-                  float scale_log2, int mufu_token) {
+                  float scale_log2, int mufu_token, int32_t* __restrict__ work_counter) {
   using L = AttnCfg<2, 2, 1, true>;
   constexpr int NKV = 2;
   griddep_launch_dependents();
@@ -576,6 +576,8 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
   uint64_t* o_full = p_full + 2;
   uint64_t* s_free = o_full + 2;  // [2] softmax(t, g) holds S(t) in registers: the next Q.K^T may overwrite it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  // the work item of ordinal n is published in item_slot[n & 1] before q_full completes phase n (-1: no more work)
+  volatile int32_t* item_slot = reinterpret_cast<volatile int32_t*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * HD;
@@ -623,13 +625,22 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         tma_load_2d(dst, &tm64, bar, col, row);
         tma_load_2d(dst + T64_BYTES, &tm64, bar, col + 64, row);
       };
+      // Work items: the first one is blockIdx.x, the following ones come from a global counter (work_counter, zero at
+      // launch) so that an SM that runs slower, or starts late, simply takes fewer items; without a counter the walk is
+      // the static stride.  Only this thread draws items; the other warps read them from item_slot.
       int g = 0, n = 0;  // global K/V block and item ordinals of this CTA
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      for (int item = blockIdx.x;; ++n) {
+        mbar_wait(q_empty, (n & 1) ^ 1);
+        item_slot[n & 1] = item;
+        if (item < 0) {
+          mbar_arrive(q_full);  // publishes the end marker
+          break;
+        }
         const AttnTile tile = tiles[item % n_tiles];
         const int head = item / n_tiles;
-        mbar_wait(q_empty, (n & 1) ^ 1);
         mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
         for (int t = 0; t < 2; ++t) load_tile(smem + L::OFF_Q + t * TILE_BYTES, q_full, head * HD, tile.q_row0 + t * QT);
+        int next = work_counter != nullptr ? static_cast<int>(gridDim.x) + atomicAdd(work_counter, 1) : item + static_cast<int>(gridDim.x);
         for (int j = 0; j < tile.n_kv_blocks; ++j, ++g) {
           const int b = g % NKV;
           const uint32_t par = ((g / NKV) & 1) ^ 1;
@@ -641,6 +652,7 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
           mbar_arrive_expect_tx(&v_full[b], V_TILE_BYTES);
           load_v(smem + L::OFF_V + b * V_TILE_BYTES, &v_full[b], 2 * D + head * HD, row);
         }
+        item = next < n_items ? next : -1;
       }
     }
   } else if (warp <= 2) {
@@ -679,50 +691,49 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         umma_commit(&v_empty[g % NKV]);
       };
       int g = 0, n = 0;
-      int item = blockIdx.x;
 #ifdef B200_ATTN_MMA_PROBE
       long long probe_issue = 0, probe_done = 0;
       int probe_n = 0;
 #endif
-      if (item < n_items) {
-        int nblk = tiles[item % n_tiles].n_kv_blocks;
-        mbar_wait(q_full, 0);
-        mbar_wait(&k_full[0], 0);
-        tc_fence_after();
-        issue_qk(0);
-        if (nblk == 1) umma_commit(q_empty);
-        while (item < n_items) {
-          const int next_item = item + gridDim.x;
-          const int next_nblk = next_item < n_items ? tiles[next_item % n_tiles].n_kv_blocks : 0;
-          for (int i = 0; i < nblk; ++i, ++g) {
-            // the successor block's Q.K^T first: it only needs S(t) back, not P(t, g)
-            const bool in_item = i + 1 < nblk;
-            if (in_item || next_nblk > 0) {
-              mbar_wait(&s_free[t], g & 1);
-              if (!in_item) mbar_wait(q_full, (n + 1) & 1);
-              mbar_wait(&k_full[(g + 1) % NKV], ((g + 1) / NKV) & 1);
-              tc_fence_after();
-              issue_qk(g + 1);
-              if (in_item ? (i + 2 == nblk) : (next_nblk == 1)) umma_commit(q_empty);  // that was the last Q.K^T of its item
-            }
-            mbar_wait(&v_full[g % NKV], (g / NKV) & 1);
-            mbar_wait(&p_full[t], g & 1);
-            tc_fence_after();
-#ifdef B200_ATTN_MMA_PROBE
-            const long long c0 = clock64();
-            issue_pv(g, i == 0);
-            const long long c1 = clock64();
-            mbar_wait(&o_full[t], g & 1);
-            const long long c2 = clock64();
-            probe_issue += c1 - c0, probe_done += c2 - c0, ++probe_n;
-#else
-            issue_pv(g, i == 0);
-#endif
+      mbar_wait(q_full, 0);
+      int nblk = tiles[item_slot[0] % n_tiles].n_kv_blocks;  // the first item always exists (grid <= items)
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      if (nblk == 1) umma_commit(q_empty);
+      while (nblk > 0) {
+        int next_nblk = 0;
+        for (int i = 0; i < nblk; ++i, ++g) {
+          // the successor block's Q.K^T first: it only needs S(t) back, not P(t, g)
+          const bool in_item = i + 1 < nblk;
+          if (!in_item) {  // the successor is the next item's first block, if there is a next item
+            mbar_wait(q_full, (n + 1) & 1);
+            const int next_item = item_slot[(n + 1) & 1];
+            next_nblk = next_item >= 0 ? tiles[next_item % n_tiles].n_kv_blocks : 0;
           }
-          item = next_item;
-          nblk = next_nblk;
-          ++n;
+          if (in_item || next_nblk > 0) {
+            mbar_wait(&s_free[t], g & 1);
+            mbar_wait(&k_full[(g + 1) % NKV], ((g + 1) / NKV) & 1);
+            tc_fence_after();
+            issue_qk(g + 1);
+            if (in_item ? (i + 2 == nblk) : (next_nblk == 1)) umma_commit(q_empty);  // that was the last Q.K^T of its item
+          }
+          mbar_wait(&v_full[g % NKV], (g / NKV) & 1);
+          mbar_wait(&p_full[t], g & 1);
+          tc_fence_after();
+#ifdef B200_ATTN_MMA_PROBE
+          const long long c0 = clock64();
+          issue_pv(g, i == 0);
+          const long long c1 = clock64();
+          mbar_wait(&o_full[t], g & 1);
+          const long long c2 = clock64();
+          probe_issue += c1 - c0, probe_done += c2 - c0, ++probe_n;
+#else
+          issue_pv(g, i == 0);
+#endif
         }
+        nblk = next_nblk;
+        ++n;
       }
 #ifdef B200_ATTN_MMA_PROBE
       if (blockIdx.x == 1) printf("mma warp %d: P.V issue %lld cycles, issue->complete %lld cycles (avg of %d)\n", t, probe_issue / probe_n, probe_done / probe_n, probe_n);
@@ -754,7 +765,10 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
 #define TSTAMP2(k)
 #endif
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int n = 0;; ++n) {
+      mbar_wait(q_full, n & 1);
+      const int item = item_slot[n & 1];
+      if (item < 0) break;
       const AttnTile tile = tiles[item % n_tiles];
       const int head = item / n_tiles;
       const int nblk = tile.n_kv_blocks;
@@ -807,10 +821,11 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
         l_part *= alpha;
         float sum = 0.f;
         uint32_t pk[SC / 2];  // this thread's probabilities, bf16
-        // MUFU token of the sub-partition.  Its two softmax warps (one per query tile) otherwise drift into lockstep: both
-        // in the exp2 pass at once, sharing the one MUFU, then both in their MUFU-free phases with the unit idle (ncu:
-        // 47 % of their samples on MUFU.EX2, the pipe 45 % busy).  Alternating, one warp's exp2 pass runs underneath the
-        // other's P store / S load / row maximum.  Worth 3 % -- a single warp cannot keep the MUFU full either.
+        // Optional MUFU token of the sub-partition (B200VIT_ATTN_TOKEN=1).  Its two softmax warps (one per query tile)
+        // drift into lockstep: both in the exp2 pass at once, sharing the one MUFU, then both in their MUFU-free phases with
+        // the unit idle (ncu: 47 % of their samples on MUFU.EX2, the pipe 45 % busy).  Alternating them is worth 5 % stand-
+        // alone and 1.5 % inside the tower on most boxes, but on one box it cost 14 % (strict alternation amplifies any
+        // stall of either tile), so it is off by default.
         if (mufu_token && (t == 1 || g > 0)) named_barrier(tok_mine, 64);
 #pragma unroll
         for (int c = 0; c < SC; c += 32) {
@@ -845,9 +860,7 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
             }
           }
         }
-        // hand the token over; tile 1's very last pass has nobody left to hand it to
-        if (mufu_token && !(t == 1 && j + 1 == nblk && item + static_cast<int>(gridDim.x) >= n_items))
-          asm volatile("bar.arrive %0, 64;" ::"r"(tok_other) : "memory");
+        if (mufu_token) asm volatile("bar.arrive %0, 64;" ::"r"(tok_other) : "memory");  // hand the token over
         TSTAMP2(4);
         if (j >= 1) {
           // every probability of the block is computed: only now is P.V(g-1) needed (P may be overwritten, O is at rest)
@@ -928,6 +941,8 @@ attn_full_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant
       }
       TSTAMP2(0);
     }  // items of this CTA
+    // tile 1's last hand-over has no taker: tile 0 absorbs it so that no barrier is left half-arrived
+    if (mufu_token && t == 0 && g > 0) named_barrier(tok_mine, 64);
     if (lane == 0) bulk_wait<0>();  // output stores have landed before the CTA exits
 #ifdef B200_ATTN_TIMING
     if (trec) printf("full attention softmax warp %d (%d blocks, %d rescales): other+store %lld | wait_s %lld | ld+max %lld | - %lld | exps %lld | wait_pv %lld | rescale %lld | store+arrive %lld | final O %lld\n",
@@ -985,7 +1000,8 @@ void build_attn_tiles(const std::vector<int32_t>& cu, int m_rows, int rows_per_t
 
 // rows_per_tile = 128 (window layers) or 256 (full layers), matching how `d_tiles` was built
 int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int n_tiles, int rows_per_tile, int max_blocks,
-                        const int32_t* d_bounds, int m_rows, int heads, cudaStream_t stream, AttnPrepared* cache) {
+                        const int32_t* d_bounds, int m_rows, int heads, cudaStream_t stream, AttnPrepared* cache,
+                        int32_t* work_counter) {
   if (n_tiles <= 0) return 0;
   AttnPrepared local;
   AttnPrepared& g = cache ? *cache : local;
@@ -1009,7 +1025,7 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
       const char* e = getenv("B200VIT_ATTN_FULL_GENERIC");  // debugging: the generic kernel's two-tile variant
       generic = (e != nullptr && e[0] == '1') ? 1 : 0;
       e = getenv("B200VIT_ATTN_TOKEN");
-      token = (e != nullptr && e[0] == '0') ? 0 : 1;
+      token = (e != nullptr && e[0] == '1') ? 1 : 0;  // off by default, see the exp2 pass
     }
     if (generic) return launch_variant<2, 2, 1, true>(g, d_tiles, n_tiles, bd, m_rows, heads, 1, scale_log2, stream);
     using L = AttnCfg<2, 2, 1, true>;
@@ -1019,9 +1035,21 @@ int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int
       attr.mark();
     }
     const int n_items = n_tiles * heads;
-    const int grid = n_items < device_sm_count() ? n_items : device_sm_count();  // persistent: one CTA per SM
+    int grid = n_items < device_sm_count() ? n_items : device_sm_count();  // persistent: one CTA per SM
+    static int one_item = -1;
+    if (one_item < 0) {
+      const char* e = getenv("B200VIT_ATTN_ONE_ITEM");  // experiment: one CTA per item (hardware-balanced)
+      one_item = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (one_item) grid = n_items;
+    static int static_walk = -1;
+    if (static_walk < 0) {
+      const char* e = getenv("B200VIT_ATTN_STATIC");  // experiment: static stride instead of the work counter
+      static_walk = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (static_walk) work_counter = nullptr;
     B200_CUDA_OK(launch_kernel(attn_full_kernel, dim3(grid), dim3(F_THREADS), L::BYTES, stream, 1, g.tm64, g.tm16, g.to64, g.to16,
-                               d_tiles, n_tiles, bd, m_rows, heads, scale_log2, token));
+                               d_tiles, n_tiles, bd, m_rows, heads, scale_log2, token, work_counter));
     return 0;
   }
   if (rows_per_tile != 128) return fail(B200VIT_EINVAL, "attention: rows_per_tile must be 128 or 256");

@@ -76,7 +76,8 @@ struct AttnPrepared {  // host memo of the two tensor maps over the qkv buffer
 void build_attn_tiles(const std::vector<int32_t>& cu, int m_rows, int rows_per_tile, std::vector<AttnTile>& tiles,
                       std::vector<int32_t>& bounds);
 int launch_attention_tc(const void* qkv, void* out, const AttnTile* d_tiles, int n_tiles, int rows_per_tile, int max_blocks,
-                        const int32_t* d_bounds, int m_rows, int heads, cudaStream_t stream, AttnPrepared* cache);
+                        const int32_t* d_bounds, int m_rows, int heads, cudaStream_t stream, AttnPrepared* cache,
+                        int32_t* work_counter = nullptr);  // full layers: a zeroed device int -> dynamic work items
 
 struct OverlayDev;  // device-side overlay description (overlay.cu)
 int launch_overlay_patchify(const b200vit_frames& fr, const b200vit_overlay* ov, int patch, int tps, int merge,
