@@ -6,7 +6,7 @@ TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 KREGEX='regex:gemm_tcgen05|attn_tc|attn_full_kernel|rmsnorm_kernel|overlay_patchify|cast_bf16|raster_kernel'
-if [ -z "$ONLY_CAPS" ]; then
+if [ -z "$NO_LAUNCH_LIST" ]; then
 # ---- launch list: skip the warm-up forwards (138 launches each incl. none from torch), take two forwards
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 552 -c 276 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline > $OUT/${TAG}_launches_bench.log 2>&1
@@ -33,13 +33,16 @@ with open(sys.argv[2], "w") as f:
 print("  ->", sys.argv[2])
 PY
 }
-cap gateup 'gemm_tcgen05' 8 python tools/prof_gemm.py gateup 2
-cap qkv_winattn 'gemm_tcgen05' 8 python tools/prof_gemm.py qkvwin 2
-cap qkv 'gemm_tcgen05' 8 python tools/prof_gemm.py qkv 2
-cap proj 'gemm_tcgen05' 8 python tools/prof_gemm.py proj 2
-cap down 'gemm_tcgen05' 8 python tools/prof_gemm.py down 2
-if [ -z "$ONLY_CAPS" ]; then
-cap attn_full 'attn_full_kernel' 4 python tools/prof_attn.py 1024 2
-cap overlay 'overlay_patchify' 6 python tools/prof_overlay.py
-fi
+CAPS=${CAPS:-"gateup qkv_winattn qkv proj down attn_full overlay"}   # which --set full captures to take
+for c in $CAPS; do
+  case $c in
+    gateup)      cap gateup 'gemm_tcgen05' 8 python tools/prof_gemm.py gateup 2 ;;
+    qkv_winattn) cap qkv_winattn 'gemm_tcgen05' 8 python tools/prof_gemm.py qkvwin 2 ;;
+    qkv)         cap qkv 'gemm_tcgen05' 8 python tools/prof_gemm.py qkv 2 ;;
+    proj)        cap proj 'gemm_tcgen05' 8 python tools/prof_gemm.py proj 2 ;;
+    down)        cap down 'gemm_tcgen05' 8 python tools/prof_gemm.py down 2 ;;
+    attn_full)   cap attn_full 'attn_full_kernel' 4 python tools/prof_attn.py 1024 2 ;;
+    overlay)     cap overlay 'overlay_patchify' 6 python tools/prof_overlay.py ;;
+  esac
+done
 ls -la $OUT | grep ${TAG}_ | head -40
