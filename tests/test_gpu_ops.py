@@ -337,6 +337,34 @@ def test_attention_varlen(lens, heads):
     close(out, ref, 1e-2)
 
 
+@pytest.mark.parametrize("lens", [[1024], [2304], [640, 1024, 384]])
+def test_attention_growing_row_maximum(lens):
+    """Full-attention kernel with the lazy row maximum: keys get larger from one 128-key block to the next (and a few
+    rows have outlier queries), so rows DO outgrow the maximum they were using by more than 2^8 several times and the
+    rescale of O in TMEM (tcgen05.ld -> scale -> tcgen05.st) and of the running sum is exercised; also a segment whose
+    first blocks are tiny so that the late maximum dominates the result (HF :182-204 softmax in fp32)."""
+    heads = 2
+    m, d = sum(lens), heads * 80
+    g = torch.Generator().manual_seed(77)
+    q = torch.randn(m, heads, 80, generator=g)
+    k = torch.randn(m, heads, 80, generator=g)
+    v = torch.randn(m, heads, 80, generator=g)
+    ramp = (1.0 + 3.0 * (torch.arange(m) // 128 % 6).float()).view(m, 1, 1)      # block b of 128 keys scaled by 1, 4, 7, ...
+    k = k * ramp
+    q[::7] *= 4.0                                                              # outlier rows: logit ranges of hundreds
+    k[: 128 * 2] *= 0.05                                                       # the first two blocks hardly matter
+    qkv = torch.stack([q, k, v], 1).reshape(m, 3 * d).to(torch.bfloat16).to(DEV)
+    out = torch.zeros(m, d, dtype=torch.bfloat16, device=DEV)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    _lib.check(_lib.lib().b200vit_attention(qkv.data_ptr(), out.data_ptr(), cu.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            len(lens), heads, _stream()), "attention")
+    torch.cuda.synchronize()
+    qf, kf, vf = qkv.float().cpu().reshape(m, 3, heads, 80).unbind(1)
+    ref = tower_ref.varlen_attention_ref(qf, kf, vf, cu, 80 ** -0.5)
+    assert torch.isfinite(out.float()).all()
+    close(out, ref, 1e-2)
+
+
 def test_attention_empty_segment_list():
     qkv = rnd((64, 3 * 160), 31)
     out = torch.zeros(64, 160, dtype=torch.bfloat16, device=DEV)
