@@ -1,6 +1,9 @@
 #!/bin/bash
-# Same-box A/B: round-1 library (_ab/r1) vs the working tree, bench.py resident numbers + per-kernel breakdown.
+# Same-box A/B: the round-1 library vs the working tree, bench.py resident numbers + per-kernel breakdown.
 # usage: tools/ab.sh [steps]   (writes gpurun_out/ab_*.json)
+# The round-1 build lives in _ab/r1 (git-ignored, travels with gpurun):
+#   git worktree add _ab/r1 8246226 && (cd _ab/r1 && python rga3-release_b200/build.py)
+# For A/B of env switches or tagged builds of THIS tree use tools/ab_tower.sh.
 S=${1:-30}
 mkdir -p gpurun_out
 summ() { python - "$1" <<'PY'
@@ -13,8 +16,7 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-if [ -d _ab/r1 ]; then (cd _ab/r1 && python bench.py --no-cpu-baseline --steps $S > ../../gpurun_out/ab_r1.json 2> ../../gpurun_out/ab_r1.err); summ gpurun_out/ab_r1.json; fi
-for v in ${VARIANTS:-0 1 2}; do
-  B200VIT_RESID_VARIANT=$v python bench.py --no-cpu-baseline --steps $S > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err; summ gpurun_out/ab_v$v.json
-done
-if [ -d _ab/r1 ]; then (cd _ab/r1 && python bench.py --no-cpu-baseline --steps $S > ../../gpurun_out/ab_r1b.json 2> ../../gpurun_out/ab_r1b.err); summ gpurun_out/ab_r1b.json; fi
+run_r1() { if [ -d _ab/r1 ]; then (cd _ab/r1 && python bench.py --no-cpu-baseline --steps $S > ../../gpurun_out/ab_r1$1.json 2> ../../gpurun_out/ab_r1$1.err); summ gpurun_out/ab_r1$1.json; fi; }
+run_r1 ""
+python bench.py --no-cpu-baseline --no-gpu-baseline --steps $S > gpurun_out/ab_now.json 2> gpurun_out/ab_now.err; summ gpurun_out/ab_now.json
+run_r1 b
