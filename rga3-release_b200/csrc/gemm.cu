@@ -48,7 +48,8 @@ struct GemmParams {
   const float2* rope;     // [P, 20] fp32 (cos, sin) of coordinate * inv_freq, P = largest grid side
   const int2* rope_pos;   // [M] (hpos, wpos) of every row
   int m, n, k, ldo;
-  int stream_k;  // bit 0: stream-K decomposition (BIAS_RESIDUAL_NORM only); bit 1: no weight prefetch before the PDL wait
+  int stream_k;  // bit 0: stream-K decomposition (BIAS_RESIDUAL_NORM only); bit 1: no weight prefetch before the PDL wait;
+                 // bit 2: QKV_ROPE_WINATTN does NOT hold the tcgen05 issue back while its warp-level MMAs run
   // fused RMSNorm (HF :57-71): RMSNorm(x) W^T == rstd(x) * (x (W diag(gamma))^T).  Producers of the fp32 residual
   // stream also emit its bf16 copy (the next GEMM's A operand) and per-row partial sums of x^2, one per 128-column
   // group, laid out [part][M]; consumers add the partials in index order and scale their accumulator rows by rstd.
@@ -428,6 +429,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // QKV_ROPE_WINATTN: raised by the leader CTA's epilogue while its warp-level MMAs run; the MMA thread holds the tcgen05
+  // issue back meanwhile (see the epilogue)
+  volatile uint32_t* hmma_gate = tmem_slot + 1;
 
   griddep_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -454,6 +458,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4 * EG * NCTA);  // one arrival per epilogue warp of every CTA
     }
+    *hmma_gate = 0;
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -541,8 +546,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       WorkIter work(num_tiles, num_kb, unit, num_units, (p.stream_k & 1) != 0);
       Segment sg;
 #ifdef B200_GEMM_TIMING
-      long long t_acc = 0, t_full = 0, t_issue = 0, t_prev = clock64(), t_start = t_prev;
-      int n_seg = 0, n_kb = 0;
+      long long t_acc = 0, t_full = 0, t_issue = 0, t_gate = 0, t_prev = clock64(), t_start = t_prev;
+      int n_seg = 0, n_kb = 0, n_held = 0;
 #define GSTAMP(v) do { long long _n = clock64(); v += _n - t_prev; t_prev = _n; } while (0)
 #else
 #define GSTAMP(v)
@@ -560,11 +565,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const uint32_t tacc = tmem_base + as * C::ACC_STRIDE;
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           GSTAMP(t_issue);
+          // the gate is sampled BEFORE the stage wait: a shared-memory load takes ~200 cycles while the operand traffic
+          // saturates the port, and behind the wait it would sit on the issue path of every k-block
+          uint32_t gate_up = 0;
+          if constexpr (EPI == B200VIT_EPI_QKV_ROPE_WINATTN) gate_up = *hmma_gate;
 #ifndef B200_GEMM_DBG_NOTMA
           mbar_wait(&full[s], ph);
           tc_fence_after();
 #endif
           GSTAMP(t_full);
+          if constexpr (EPI == B200VIT_EPI_QKV_ROPE_WINATTN) {
+            if (gate_up != 0) {
+#ifdef B200_GEMM_TIMING
+              ++n_held;
+#endif
+              while (*hmma_gate != 0) {  // the epilogue's mma.sync section has the tensor cores to itself
+              }
+            }
+            GSTAMP(t_gate);
+          }
           const uint32_t a_addr = smem_u32(sA + s * C::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
 #pragma unroll
@@ -588,8 +607,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
 #ifdef B200_GEMM_TIMING
       GSTAMP(t_issue);
-      if (blockIdx.x == 10) printf("gemm mma thread: %d segs %d kb | total %lld | wait tempty %lld | wait full %lld | issue %lld\n",
-                                   n_seg, n_kb, clock64() - t_start, t_acc, t_full, t_issue);
+      if (blockIdx.x == 10) printf("gemm mma thread: %d segs %d kb | total %lld | wait tempty %lld | wait full %lld | issue %lld | held by the epilogue %lld (%d times)\n",
+                                   n_seg, n_kb, clock64() - t_start, t_acc, t_full, t_issue, t_gate, n_held);
 #endif
     }
   } else if (warp >= 4) {
@@ -612,8 +631,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // head-interleaved, so the 240 columns of a tile are Q_h | K_h | V_h of one head h, and a CTA's 128 rows are two
       // 64-patch windows: everything softmax(Q K^T / sqrt(80)) V needs for (2 windows x 1 head) is in this CTA's
       // accumulator.  The 12 epilogue warps stage Q, K (rotated) and V as bf16 in shared memory exactly as the plain
-      // epilogue does -- and then, instead of storing them, four warps run the attention of 32 query rows each with
-      // warp-level MMAs (5.2 MFLOP per tile against 78.6 MFLOP of projection) and store the 32 x 80 output rows.
+      // epilogue does -- and then, instead of storing them, eight warps run the attention of 16 query rows each with
+      // warp-level MMAs (5.2 MFLOP per tile against 78.6 MFLOP of projection) and store the output rows.
       // Q, K, V never reach L2 / HBM (63 MB written and read back per layer otherwise) and the 28 attention launches
       // disappear.  Overlaps the next tile's main loop like every other epilogue.
       static_assert(CW == 80 && EG == 3, "one head per tile: Q | K | V groups of 80 columns");
@@ -644,108 +663,109 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         ESTAMP(e_a);
         named_barrier(1, EPI_THREADS);  // Q, K, V of the CTA's two windows are staged
+        // mma.sync and tcgen05.mma share the tensor cores, and while the main loop runs the warp-level MMAs get ~1/8 of
+        // their stand-alone rate (70 cycles per HMMA and sub-partition, whether four warps or eight issue them): 11 k
+        // cycles of attention per tile against a 10 k cycle main loop that cannot hide them.  So the leader CTA's
+        // epilogue raises a gate that holds the tcgen05 issue back for the few thousand cycles the section then needs
+        // (the partner CTA's section runs at the same time: both are released by the same multicast commit).
+        const bool gate_owner = rank == 0 && warp == 4 && lane == 0 && !(p.stream_k & 4);
+        if (gate_owner) *hmma_gate = 1;
+#ifdef B200_GEMM_TIMING
+        const long long gate_t0 = clock64();
+#endif
         ESTAMP(e_b);
-        // The GEMM main loop keeps shared memory at its bandwidth limit (TMA writes + operand reads), so the attention
-        // is organised to touch it as little as possible: ONE warp per 32 query rows (the Q warp of each quadrant, on its
-        // own staged rows), so every K / V fragment is read twice per window instead of four times.
-        uint32_t opk[2][20];            // this warp's 32 x 80 output, bf16 pairs: [m tile][dim tile][row half]
-        if (g == 0) {
-          const int w = q >> 1;         // window (rows 64 w .. 64 w + 63 of the CTA) of this warp's 32 query rows
-          const uint32_t qb = stg;      // this warp staged exactly the Q rows it now consumes
+        // The epilogue, not the main loop, is what this kernel waits for (MMA-thread clocks: 33 k of 116 k cycles blocked on
+        // tempty when four warps ran the attention, 11 k cycles per tile at ~70 cycles per dependent ldmatrix -> HMMA step
+        // under the main loop's saturated shared-memory port).  So EIGHT warps run it, 16 query rows each: warp (g, q),
+        // g < 2, takes rows 16 g .. 16 g + 15 of quadrant q's 32 staged Q rows.  K / V fragments are read once per warp
+        // (four times per window instead of twice): +80 KB of ldmatrix traffic per tile against 1.6 MB of operand traffic.
+        uint32_t opk[20];              // this warp's 16 x 80 output, bf16 pairs: [dim tile][row half]
+        const uint32_t qbuf = stg_all + q * C::STG_WARP;  // quadrant q's Q rows (staged by warp (0, q)); later its output tile
+        if (g < 2) {
+          const int w = q >> 1;         // window (rows 64 w .. 64 w + 63 of the CTA) of this warp's query rows
+          const uint32_t qb = qbuf + 16 * g * RS;
           const int lr = (lane & 7) + 8 * ((lane >> 3) & 1), lc = lane >> 4;     // ldmatrix address roles
-          float sacc[2][8][4];
+          float sacc[8][4];
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sacc[mt][i][0] = sacc[mt][i][1] = sacc[mt][i][2] = sacc[mt][i][3] = 0.f;
+          for (int i = 0; i < 8; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
 #pragma unroll
           for (int ks = 0; ks < 5; ++ks) {  // S = Q K^T over the 80 head dims, 16 at a time
-            uint32_t a[2][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-              ldmatrix_x4(qb + (16 * mt + lr) * RS + (ks * 16 + 8 * lc) * 2, a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+            uint32_t a[4];
+            ldmatrix_x4(qb + lr * RS + (ks * 16 + 8 * lc) * 2, a[0], a[1], a[2], a[3]);
 #pragma unroll
             for (int nt = 0; nt < 8; nt += 2) {  // keys 8 nt .. 8 nt + 15
               const uint32_t kb = stg_all + (1 * 4 + 2 * w + (nt >> 2)) * C::STG_WARP + ((8 * nt) & 31) * RS;
               uint32_t b0, b1, b2, b3;
               ldmatrix_x4(kb + ((lane & 7) + 8 * lc) * RS + (ks * 16 + 8 * ((lane >> 3) & 1)) * 2, b0, b1, b2, b3);
-#pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                mma_bf16_16816(sacc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
-                mma_bf16_16816(sacc[mt][nt + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b2, b3);
-              }
+              mma_bf16_16816(sacc[nt], a[0], a[1], a[2], a[3], b0, b1);
+              mma_bf16_16816(sacc[nt + 1], a[0], a[1], a[2], a[3], b2, b3);
             }
           }
-          // softmax over the window's 64 keys; a thread holds rows lane/4 and lane/4 + 8 of each m tile, a quad a whole row
-          uint32_t pa[2][4][4];  // P as A operands of the four 16-key steps
-          float inv[2][2];
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
+          // softmax over the window's 64 keys; a thread holds rows lane/4 and lane/4 + 8, a quad a whole row
+          uint32_t pa[4][4];  // P as A operands of the four 16-key steps
+          float inv[2];
+          {
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              mx0 = fmaxf(mx0, fmaxf(sacc[mt][i][0], sacc[mt][i][1]));
-              mx1 = fmaxf(mx1, fmaxf(sacc[mt][i][2], sacc[mt][i][3]));
+              mx0 = fmaxf(mx0, fmaxf(sacc[i][0], sacc[i][1]));
+              mx1 = fmaxf(mx1, fmaxf(sacc[i][2], sacc[i][3]));
             }
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
             float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float e0 = ex2f((sacc[mt][i][0] - mx0) * scale_log2), e1 = ex2f((sacc[mt][i][1] - mx0) * scale_log2);
-              const float e2 = ex2f((sacc[mt][i][2] - mx1) * scale_log2), e3 = ex2f((sacc[mt][i][3] - mx1) * scale_log2);
+              const float e0 = ex2f((sacc[i][0] - mx0) * scale_log2), e1 = ex2f((sacc[i][1] - mx0) * scale_log2);
+              const float e2 = ex2f((sacc[i][2] - mx1) * scale_log2), e3 = ex2f((sacc[i][3] - mx1) * scale_log2);
               sum0 += e0 + e1, sum1 += e2 + e3;
-              pa[mt][i >> 1][(i & 1) * 2] = pack_bf16x2(e0, e1);
-              pa[mt][i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(e2, e3);
+              pa[i >> 1][(i & 1) * 2] = pack_bf16x2(e0, e1);
+              pa[i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(e2, e3);
             }
             sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1), sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
             sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1), sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-            inv[mt][0] = 1.0f / sum0, inv[mt][1] = 1.0f / sum1;
+            inv[0] = 1.0f / sum0, inv[1] = 1.0f / sum1;
           }
 #pragma unroll
-          for (int dp = 0; dp < 5; ++dp) {  // O = P V, two 8-wide dim tiles per pass (register pressure)
-            float oacc[2][2][4];
+          for (int dp = 0; dp < 5; ++dp) {  // O = P V, two 8-wide dim tiles per pass
+            float oacc[2][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-              for (int i = 0; i < 2; ++i) oacc[mt][i][0] = oacc[mt][i][1] = oacc[mt][i][2] = oacc[mt][i][3] = 0.f;
+            for (int i = 0; i < 2; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {  // keys 16 j .. 16 j + 15
               const uint32_t vb = stg_all + (2 * 4 + 2 * w + (j >> 1)) * C::STG_WARP + ((16 * j) & 31) * RS;
               uint32_t b0, b1, b2, b3;
               ldmatrix_x4_trans(vb + lr * RS + (dp * 16 + 8 * lc) * 2, b0, b1, b2, b3);
-#pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                mma_bf16_16816(oacc[mt][0], pa[mt][j][0], pa[mt][j][1], pa[mt][j][2], pa[mt][j][3], b0, b1);
-                mma_bf16_16816(oacc[mt][1], pa[mt][j][0], pa[mt][j][1], pa[mt][j][2], pa[mt][j][3], b2, b3);
-              }
+              mma_bf16_16816(oacc[0], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b0, b1);
+              mma_bf16_16816(oacc[1], pa[j][0], pa[j][1], pa[j][2], pa[j][3], b2, b3);
             }
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                opk[mt][(dp * 2 + i) * 2] = pack_bf16x2(oacc[mt][i][0] * inv[mt][0], oacc[mt][i][1] * inv[mt][0]);
-                opk[mt][(dp * 2 + i) * 2 + 1] = pack_bf16x2(oacc[mt][i][2] * inv[mt][1], oacc[mt][i][3] * inv[mt][1]);
-              }
+            for (int i = 0; i < 2; ++i) {
+              opk[(dp * 2 + i) * 2] = pack_bf16x2(oacc[i][0] * inv[0], oacc[i][1] * inv[0]);
+              opk[(dp * 2 + i) * 2 + 1] = pack_bf16x2(oacc[i][2] * inv[1], oacc[i][3] * inv[1]);
+            }
           }
         }
         ESTAMP(e_c);
         named_barrier(2, EPI_THREADS);  // every read of the staged Q, K, V is done: the buffers may be reused
+        if (gate_owner) *hmma_gate = 0;
+#ifdef B200_GEMM_TIMING
+        if (gate_owner && blockIdx.x == 10) printf("gate up %lld cycles\n", clock64() - gate_t0);
+#endif
         ESTAMP(e_b);
-        if (g == 0) {
-          // 32 x 80 bf16, dense 160-byte rows at the start of this warp's own buffer -> one TMA store
+        if (g < 2) {
+          // 32 x 80 bf16 per quadrant, dense 160-byte rows at the start of the Q warp's buffer (rows 16 g .. from this
+          // warp) -> one TMA store by the Q warp once both halves are in
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int i = 0; i < 10; ++i) {
-              const uint32_t base = stg + (16 * mt + (lane >> 2)) * 160 + (i * 8 + 2 * (lane & 3)) * 2;
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(base), "r"(opk[mt][2 * i]) : "memory");
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 8 * 160), "r"(opk[mt][2 * i + 1]) : "memory");
-            }
+          for (int i = 0; i < 10; ++i) {
+            const uint32_t base = qbuf + (16 * g + (lane >> 2)) * 160 + (i * 8 + 2 * (lane & 3)) * 2;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base), "r"(opk[2 * i]) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 8 * 160), "r"(opk[2 * i + 1]) : "memory");
+          }
           fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tma_out, stg, head * 80, m0 + q * 32);
+          named_barrier(3 + q, 64);
+          if (g == 0 && lane == 0) {
+            tma_store_2d(&tma_out, qbuf, head * 80, m0 + q * 32);
             bulk_commit();
           }
         }
@@ -943,6 +963,15 @@ bool stream_k_enabled() {
   return v == 1;
 }
 
+bool winattn_gate_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200VIT_WINATTN_GATE");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 bool weight_prefetch_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1011,7 +1040,7 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
   }
   GemmParams p{a.d_out, a.d_bias, a.d_row_map, reinterpret_cast<const float2*>(a.d_rope),
                reinterpret_cast<const int2*>(a.d_rope_pos), a.m, a.n, a.k, a.ldo,
-               g.stream_k | (weight_prefetch_enabled() ? 0 : 2),
+               g.stream_k | (weight_prefetch_enabled() ? 0 : 2) | (winattn_gate_enabled() ? 0 : 4),
                reinterpret_cast<__nv_bfloat16*>(a.d_out_bf16), a.d_rowsq_out, a.d_rowsq_in, a.rowsq_parts, a.norm_eps, a.d_sync};
   auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
   static DeviceOnce attr_set;  // per instantiation and device
