@@ -535,7 +535,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 
 // ------------------------------------------------------------------ full-attention layers (persistent)
 // Two 128-row query tiles of one head share each K/V block (as attn_tc_kernel<2, 2, 1, true>), one thread per query row,
-// with four changes that each came out of a measurement:
+// with changes that each came out of a measurement:
 //  * O stays in TMEM for the whole K/V walk: P.V(j) accumulates onto P.V(j-1) and the softmax warps never read a
 //    per-block O back.  The running maximum is therefore LAZY: a row keeps the maximum m it has used so far while the
 //    new block's maximum stays below m + 8 (log2 units; P <= 2^8, harmless in bf16 / fp32), and only when it grows past
@@ -547,8 +547,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 //    after the whole exp2 pass, just before P is overwritten.
 //  * one MMA-issuing warp per tile on blocking (hardware-suspended) mbarrier waits.  (A single issuer polling both tiles
 //    with nanosleep between probes reacted late: the sleep quantum is ~1 us.)
-//  * PERSISTENT: one CTA per SM walks work items (256-row tile pair, head), item = blockIdx.x + k * gridDim.x, tile
-//    index fastest (co-resident CTAs share a head's K/V in L2).  Barrier phases run on global block / item counters, so
+//  * PERSISTENT: one CTA per SM walks work items (256-row tile pair, head) -- the first is blockIdx.x, the following
+//    ones are drawn from a device counter (or blockIdx.x + k * gridDim.x without one) -- tile index fastest
+//    (co-resident CTAs share a head's K/V in L2).  Barrier phases run on global block / item counters, so
 //    the K/V ring, S and P flow straight across item boundaries: the next item's Q is loaded as soon as the last Q.K^T
 //    of the current one has been issued, its first Q.K^T runs underneath the current item's last softmax, and an item's
 //    output store drains while the next item's first block is computed.
