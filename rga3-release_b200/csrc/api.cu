@@ -653,11 +653,17 @@ int b200vit_attention(const void* d_qkv, void* d_out, const int32_t* h_cu_seqlen
   B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_bounds), bounds.size() * sizeof(int32_t)));
   B200_CUDA_OK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(AttnTile), cudaMemcpyHostToDevice, stream));
   B200_CUDA_OK(cudaMemcpyAsync(d_bounds, bounds.data(), bounds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  int32_t* d_counter = nullptr;  // full-attention kernel: work items drawn from a zeroed counter, as in b200vit_forward
+  if (rows_per_tile == 256) {
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_counter), sizeof(int32_t)));
+    B200_CUDA_OK(cudaMemsetAsync(d_counter, 0, sizeof(int32_t), stream));
+  }
   rc = launch_attention_tc(d_qkv, d_out, d_tiles, static_cast<int>(tiles.size()), rows_per_tile, maxblk, d_bounds, m_rows, heads,
-                           stream, nullptr);
+                           stream, nullptr, d_counter);
   cudaStreamSynchronize(stream);  // test entry point: the temporaries are freed before returning
   cudaFree(d_tiles);
   cudaFree(d_bounds);
+  if (d_counter) cudaFree(d_counter);
   return rc;
 }
 

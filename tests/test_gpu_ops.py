@@ -323,7 +323,8 @@ def test_rmsnorm(rows, dim):
     close(out, tower_ref.rmsnorm_ref(x.cpu(), w.cpu()), 1e-2)
 
 
-@pytest.mark.parametrize("lens,heads", [([64, 64, 32, 16, 64], 2), ([1024, 1024], 4), ([100, 7, 2304, 64, 1], 2), ([60], 16)])
+@pytest.mark.parametrize("lens,heads", [([64, 64, 32, 16, 64], 2), ([1024, 1024], 4), ([100, 7, 2304, 64, 1], 2), ([60], 16),
+                                        ([1024] * 5 + [300, 512], 16)])   # 384 work items on 148 persistent CTAs
 def test_attention_varlen(lens, heads):
     m, d = sum(lens), heads * 80
     qkv = rnd((m, 3 * d), 30, 1.0)
