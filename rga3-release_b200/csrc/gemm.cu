@@ -990,12 +990,49 @@ bool use_pair() {
   return v == 1;
 }
 
+// How many units (CTAs, or CTA pairs) of `kern` can be resident on the current device at the same time.  Queried once per
+// call-site preparation (memoised with the tensor maps); a failed query counts as "enough" (plain devices always fit one
+// CTA per SM, which is what the grids are sized for).
+template <typename K>
+int coresident_units(K kern, int threads, int smem_bytes, bool pair, int sms) {
+  if (pair) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, reinterpret_cast<const void*>(kern), &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return sms;
+    }
+    return clusters;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, static_cast<size_t>(smem_bytes)) != cudaSuccess) {
+    cudaGetLastError();
+    return sms;
+  }
+  return per_sm * sms;
+}
+
 template <int BN, int EG, int EPI, bool PAIR>
 int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* cache) {
   using C = TileCfg<BN, EG, EPI, PAIR>;
   constexpr int MT = PAIR ? 2 * BM : BM;
   GemmPrepared local;
   GemmPrepared& g = cache ? *cache : local;
+  auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
+  static DeviceOnce attr_set;  // per instantiation and device
+  if (attr_set.need()) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set.mark();
+  }
   if (!(g.valid && std::memcmp(&g.key, &a, sizeof(a)) == 0)) {
     g.valid = false;
     int rc = make_tmap_bf16(&g.ta, a.d_a, a.m, a.k, BM);
@@ -1028,8 +1065,13 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
       // cut is always between the LAST segment of unit u (head) and the FIRST segment of unit u + 1 (tail).
       const int num_kb = (a.k + BK - 1) / BK;
       const long long total = static_cast<long long>(num_tiles) * num_kb;
+      // The head of a cut tile waits for the flag of the unit that holds its tail, so every CTA of the grid must be
+      // resident at the same time: ask the occupancy calculator (it knows about MPS / green-context SM limits) and fall
+      // back to whole tiles when the grid would not fit.  The last 64 ints of the scratch are the full-attention layers'
+      // work counters (api.cu).
       if (num_tiles % max_units != 0 && total / max_units >= num_kb + 8 &&
-          (max_units + 1) * (PAIR ? 2 : 1) * C::EPI_WARPS <= B200VIT_GEMM_SYNC_INTS) {
+          (max_units + 1) * (PAIR ? 2 : 1) * C::EPI_WARPS <= B200VIT_GEMM_SYNC_INTS - 64 &&
+          coresident_units(kern, 128 + 128 * EG, C::SMEM_BYTES, PAIR, sms) >= max_units) {
         units = max_units;
         g.stream_k = 1;
       }
@@ -1042,12 +1084,6 @@ int launch_cfg(const b200vit_gemm_args& a, cudaStream_t stream, GemmPrepared* ca
                reinterpret_cast<const int2*>(a.d_rope_pos), a.m, a.n, a.k, a.ldo,
                g.stream_k | (weight_prefetch_enabled() ? 0 : 2) | (winattn_gate_enabled() ? 0 : 4),
                reinterpret_cast<__nv_bfloat16*>(a.d_out_bf16), a.d_rowsq_out, a.d_rowsq_in, a.rowsq_parts, a.norm_eps, a.d_sync};
-  auto kern = gemm_tcgen05_kernel<BN, EG, EPI, PAIR>;
-  static DeviceOnce attr_set;  // per instantiation and device
-  if (attr_set.need()) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set.mark();
-  }
   B200_CUDA_OK(launch_kernel(kern, dim3(g.grid), dim3(128 + 128 * EG), C::SMEM_BYTES, stream, PAIR ? 2 : 1, g.ta, g.tb, g.to, g.taux, p));
   return 0;
 }
